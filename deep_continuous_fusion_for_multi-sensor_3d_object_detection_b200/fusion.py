@@ -1,0 +1,129 @@
+"""The continuous-fusion layer as an nn.Module -- the layer the reference leaves as a TODO at
+model.py:199-203, inserted after residual groups of ResnetCustomed.forward (model.py:74-78).
+
+Per batch (shared by all scales, `FrameContext`):   K-1 bucket the LiDAR points, K-3 project + gather the
+camera features per point.   Per scale (`ContinuousFusion`):   K-4a per-point half of MLP layer 1, K-2 KNN
+per BEV cell, K-4 fused MLP + K-sum-pool + BEV add.   All arithmetic is in libcf_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import geometry as G
+from . import ops
+
+
+class FrameContext:
+    """Per-batch state shared by every fusion scale: bucketed points and gathered camera features."""
+
+    def __init__(self, points, num_points, grid: ops.BucketGrid):
+        if points.dim() != 3 or points.shape[-1] != 3:
+            raise ValueError(f"pointcloud_raw: expected (B,N,3), got {tuple(points.shape)}")
+        self.points = ops._contig(points, "pointcloud_raw", torch.float32, 3)
+        self.B, self.N = self.points.shape[:2]
+        self.num_points = ops.as_counts(num_points, self.B, self.points.device)
+        self.grid = grid
+        self.bucket_start, self.sorted_pts, self._bucket_ws = ops.bucket_points(self.points, self.num_points, grid)
+        self.feat = None
+        self._gather_ws = None
+        self._knn_cache = {}
+
+    def gather(self, img_feat, calib=None, uv=None, img_size=(640.0, 480.0)):
+        self.feat, self._gather_ws = ops.point_gather(img_feat, self.points, self.num_points, calib=calib, uv=uv,
+                                                      img_size=img_size, workspace=self._gather_ws)
+        return self.feat
+
+    def knn(self, H, W, geom, radius, K):
+        key = (H, W, tuple(float(g) for g in geom), float(radius), int(K))
+        if key not in self._knn_cache:
+            self._knn_cache[key] = ops.knn_query(self.bucket_start, self.sorted_pts, self.grid, H, W, geom, radius, K)
+        return self._knn_cache[key]
+
+
+def prepare_frames(points, num_points, img_feat, config=None, calib=None, uv=None, grid=None, img_size=None):
+    """Build the per-batch context: bucket points (K-1) and gather camera features (K-3)."""
+    if grid is None:
+        config = G.carla_config() if config is None else config
+        grid = ops.BucketGrid(*G.bucket_grid(config))
+    if img_size is None:
+        img_size = (float(config["image_width"]), float(config["image_height"])) if config else (640.0, 480.0)
+    ctx = FrameContext(points, num_points, grid)
+    ctx.gather(img_feat, calib=calib, uv=uv, img_size=img_size)
+    return ctx
+
+
+class _FusionFunction(torch.autograd.Function):
+    """Forward = cf_point_mlp1 + cf_fusion_fwd.  Saves indices, inputs and weights, never the gathered rows."""
+
+    @staticmethod
+    def forward(ctx, bev, feat, points, num_points, knn_idx, geom, mode, w1, b1, w2, b2, w3, b3):
+        T = ops.point_mlp1(feat, points, num_points, w1, b1)
+        out, _ = ops.fusion_fwd(bev, T, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode)
+        ctx.save_for_backward(feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3)
+        ctx.geom, ctx.mode = geom, mode
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        raise NotImplementedError(
+            "cf_fusion_bwd (SURVEY 8a row K-4b) is not built in this round; run the layer under torch.no_grad() "
+            "or with frozen fusion weights")
+
+
+class ContinuousFusion(nn.Module):
+    """out = bev + sum_{k in KNN(cell)} MLP([camera feature of point k, offset of point k to the cell]).
+
+    Parameters follow SURVEY Appendix A9: Linear(c_img+3, c_bev) - ReLU - Linear(c_bev, c_bev) - ReLU -
+    Linear(c_bev, c_bev), input order [image feature | offset].
+    `geom` = (x0, y0, dx, dy) float32 scalars of the BEV cell centres at this scale (geometry.scale_geometry).
+    """
+
+    def __init__(self, c_img: int, c_bev: int, k: int = 3, radius: float = 2.0, geom=None, mode: str = "fp32"):
+        super().__init__()
+        if not (1 <= k <= 16):
+            raise ValueError("k must be in [1, 16]")
+        if c_bev % 16 or not (16 <= c_bev <= 256):
+            raise ValueError("c_bev must be a multiple of 16 in [16, 256]")
+        if c_img % 4:
+            raise ValueError("c_img must be a multiple of 4")
+        self.c_img, self.c_bev, self.k, self.radius, self.mode = c_img, c_bev, int(k), float(radius), mode
+        self.geom = tuple(float(g) for g in geom) if geom is not None else None
+        self.fc1 = nn.Linear(c_img + 3, c_bev)
+        self.fc2 = nn.Linear(c_bev, c_bev)
+        self.fc3 = nn.Linear(c_bev, c_bev)
+
+    def extra_repr(self):
+        return f"c_img={self.c_img}, c_bev={self.c_bev}, k={self.k}, radius={self.radius}, mode={self.mode}"
+
+    def forward(self, bev, img_feat=None, points=None, num_points=None, calib=None, uv=None, frames: FrameContext = None,
+                geom=None, return_knn: bool = False):
+        geom = tuple(float(g) for g in geom) if geom is not None else self.geom
+        if geom is None:
+            raise ValueError("ContinuousFusion: BEV geometry (x0,y0,dx,dy) not set")
+        if bev.dim() != 4 or bev.shape[1] != self.c_bev:
+            raise ValueError(f"bev: expected (B,{self.c_bev},H,W), got {tuple(bev.shape)}")
+        if frames is None:
+            if img_feat is None or points is None or num_points is None:
+                raise ValueError("ContinuousFusion: pass either frames= or img_feat/points/num_points")
+            frames = prepare_frames(points, num_points, img_feat, calib=calib, uv=uv)
+        if frames.feat is None:
+            raise ValueError("ContinuousFusion: FrameContext has no gathered camera features (call .gather)")
+        if frames.feat.shape[2] != self.c_img:
+            raise ValueError(f"camera feature width {frames.feat.shape[2]} != c_img {self.c_img}")
+        B, _, H, W = bev.shape
+        knn_idx = frames.knn(H, W, geom, self.radius, self.k)
+        args = (bev, frames.feat, frames.points, frames.num_points, knn_idx, geom, self.mode, self.fc1.weight,
+                self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias)
+        needs_grad = torch.is_grad_enabled() and (bev.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            out = _FusionFunction.apply(*args)
+        else:
+            with torch.no_grad():
+                out = _FusionFunction.forward(_NullCtx(), *[a.detach() if isinstance(a, torch.Tensor) else a for a in args])
+        return (out, knn_idx) if return_knn else out
+
+
+class _NullCtx:
+    def save_for_backward(self, *a):
+        pass

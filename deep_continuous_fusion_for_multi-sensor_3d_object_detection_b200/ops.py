@@ -1,0 +1,229 @@
+"""Thin torch-tensor wrappers, one per C-ABI entry point of include/cf_b200.h.
+
+PyTorch is plumbing here: it owns device memory and the current stream; all arithmetic happens in
+libcf_b200.so.  Every wrapper validates device / dtype / contiguity and raises instead of falling back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, load, ptr, stream_ptr
+
+
+def _req(t: torch.Tensor, name: str, dtype, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: must be a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def _contig(t: torch.Tensor, name: str, dtype, ndim=None):
+    _req(t, name, dtype, ndim)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def as_counts(num_points, B: int, device) -> torch.Tensor:
+    """sample["num_points_raw"] after collation is a (B,) int64 CPU tensor (data_import_carla.py:262)."""
+    if not isinstance(num_points, torch.Tensor):
+        num_points = torch.as_tensor(np.asarray(num_points), dtype=torch.int64)
+    num_points = num_points.reshape(-1).to(device=device, dtype=torch.int64, non_blocking=True)
+    if num_points.numel() != B:
+        raise ValueError(f"num_points: expected {B} entries, got {num_points.numel()}")
+    return num_points.contiguous()
+
+
+class BucketGrid:
+    """Uniform BEV bucket grid (K-1) + the per-batch sorted point storage."""
+
+    def __init__(self, gx0, gy0, cell, nbx, nby):
+        self.gx0, self.gy0, self.cell = float(gx0), float(gy0), float(cell)
+        self.nbx, self.nby = int(nbx), int(nby)
+
+
+def bucket_points(points: torch.Tensor, num_points: torch.Tensor, grid: BucketGrid, out=None):
+    """K-1.  points (B,N,3) f32, num_points (B,) i64 -> bucket_start (B,G+1) i32, sorted (B,N,4) f32."""
+    lib = load()
+    points = _contig(points, "points", torch.float32, 3)
+    B, N, three = points.shape
+    if three != 3:
+        raise ValueError(f"points: last dim must be 3, got {three}")
+    num_points = _req(num_points, "num_points", torch.int64, 1)
+    G = grid.nbx * grid.nby
+    if out is None:
+        start = torch.empty((B, G + 1), dtype=torch.int32, device=points.device)
+        srt = torch.empty((B, N, 4), dtype=torch.float32, device=points.device)
+        ws = torch.empty((max(lib.cf_bucket_workspace_bytes(B, grid.nbx, grid.nby), 16),), dtype=torch.uint8,
+                         device=points.device)
+    else:
+        start, srt, ws = out
+    check(lib.cf_bucket_points(ptr(points), ptr(num_points), B, N, grid.gx0, grid.gy0, grid.cell, grid.nbx, grid.nby,
+                               ptr(start), ptr(srt), ptr(ws), stream_ptr()), "cf_bucket_points")
+    return start, srt, ws
+
+
+def knn_query(bucket_start, sorted_pts, grid: BucketGrid, H, W, geom, radius, K, out=None):
+    """K-2.  -> knn_idx (B,H,W,K) int32, -1 = empty slot."""
+    lib = load()
+    _req(bucket_start, "bucket_start", torch.int32, 2)
+    _req(sorted_pts, "sorted_pts", torch.float32, 3)
+    B, N, _ = sorted_pts.shape
+    x0, y0, dx, dy = [float(g) for g in geom]
+    if out is None:
+        out = torch.empty((B, H, W, K), dtype=torch.int32, device=sorted_pts.device)
+    check(lib.cf_knn_query(ptr(bucket_start), ptr(sorted_pts), B, N, grid.gx0, grid.gy0, grid.cell, grid.nbx, grid.nby,
+                           H, W, x0, y0, dx, dy, float(radius), int(K), ptr(out), stream_ptr()), "cf_knn_query")
+    return out
+
+
+def point_gather(img_feat, points, num_points, calib=None, uv=None, img_size=(640.0, 480.0), out=None, workspace=None):
+    """K-3.  img_feat logical (B,Ci,Hf,Wf) (any strides; channels_last avoids the re-layout pass),
+    points (B,N,3), exactly one of calib ((4,3) array, host) / uv ((B,N,2) device) -> feat (B,N,Ci)."""
+    lib = load()
+    _req(img_feat, "img_feat", torch.float32, 4)
+    points = _contig(points, "points", torch.float32, 3)
+    B, Ci, Hf, Wf = img_feat.shape
+    N = points.shape[1]
+    sb, sc, sh, sw = img_feat.stride()
+    if (calib is None) == (uv is None):
+        raise ValueError("pass exactly one of calib / uv")
+    calib_arr = None
+    if calib is not None:
+        calib_np = np.ascontiguousarray(calib.detach().cpu().numpy() if isinstance(calib, torch.Tensor) else calib,
+                                        dtype=np.float32)
+        if calib_np.shape != (4, 3):
+            raise ValueError(f"calib: expected (4,3) CRT_tensor, got {calib_np.shape}")
+        calib_arr = (C.c_float * 12)(*calib_np.reshape(-1).tolist())
+    else:
+        uv = _contig(uv, "uv", torch.float32, 3)
+        if uv.shape != (B, N, 2):
+            raise ValueError(f"uv: expected {(B, N, 2)}, got {tuple(uv.shape)}")
+    if out is None:
+        out = torch.empty((B, N, Ci), dtype=torch.float32, device=points.device)
+    need = lib.cf_gather_workspace_bytes(B, Ci, Hf, Wf, sc)
+    if need and (workspace is None or workspace.numel() < need):
+        workspace = torch.empty((need,), dtype=torch.uint8, device=points.device)
+    check(lib.cf_point_gather(ptr(img_feat), sb, sc, sh, sw, B, Ci, Hf, Wf, ptr(points), ptr(uv), calib_arr,
+                              ptr(num_points), N, float(img_size[0]), float(img_size[1]), ptr(out), ptr(workspace),
+                              stream_ptr()), "cf_point_gather")
+    return out, workspace
+
+
+def point_mlp1(feat, points, num_points, W1, b1, out=None):
+    """K-4a.  T (B,N,C) = feat W1[:, :Ci]^T + points W1[:, Ci:]^T + b1."""
+    lib = load()
+    feat = _contig(feat, "feat", torch.float32, 3)
+    points = _contig(points, "points", torch.float32, 3)
+    W1 = _contig(W1, "W1", torch.float32, 2)
+    b1 = _contig(b1, "b1", torch.float32, 1)
+    B, N, Ci = feat.shape
+    C_out = W1.shape[0]
+    if W1.shape[1] != Ci + 3 or b1.shape[0] != C_out:
+        raise ValueError(f"W1/b1: expected ({C_out},{Ci + 3})/({C_out},), got {tuple(W1.shape)}/{tuple(b1.shape)}")
+    if out is None:
+        out = torch.empty((B, N, C_out), dtype=torch.float32, device=feat.device)
+    check(lib.cf_point_mlp1(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, C_out, ptr(W1), ptr(b1), ptr(out),
+                            stream_ptr()), "cf_point_mlp1")
+    return out
+
+
+def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None, workspace=None):
+    """K-4.  out = bev + W3 sum_k relu(W2 relu(T[idx_k] - e_cell) + b2) + n_valid b3."""
+    lib = load()
+    bev = _contig(bev, "bev", torch.float32, 4)
+    T = _contig(T, "T", torch.float32, 3)
+    knn_idx = _contig(knn_idx, "knn_idx", torch.int32, 4)
+    B, Cc, H, W = bev.shape
+    N = T.shape[1]
+    K = knn_idx.shape[3]
+    if T.shape[0] != B or T.shape[2] != Cc or tuple(knn_idx.shape[:3]) != (B, H, W):
+        raise ValueError("fusion_fwd: inconsistent shapes")
+    W1 = _contig(W1, "W1", torch.float32, 2)
+    W2 = _contig(W2, "W2", torch.float32, 2)
+    W3 = _contig(W3, "W3", torch.float32, 2)
+    b2 = _contig(b2, "b2", torch.float32, 1)
+    b3 = _contig(b3, "b3", torch.float32, 1)
+    Ci = W1.shape[1] - 3
+    m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+    need = max(lib.cf_fusion_workspace_bytes(Cc, m), 16)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=bev.device)
+    if out is None:
+        out = torch.empty_like(bev)
+    x0, y0, dx, dy = [float(g) for g in geom]
+    check(lib.cf_fusion_fwd(ptr(bev), ptr(T), ptr(knn_idx), B, N, Cc, H, W, K, x0, y0, dx, dy, ptr(W1), Ci, ptr(W2),
+                            ptr(b2), ptr(W3), ptr(b3), ptr(out), m, ptr(workspace), stream_ptr()), "cf_fusion_fwd")
+    return out, workspace
+
+
+# ------------------------------------------------------------------------------------------ post-process
+def get_bboxes(pred_cls, pred_box, thr=0.8, cap=4096):
+    """P-1.  (B,4,H,W), (B,14,H,W) -> boxes (B,cap,7), counts (B,) i32 (clamped), counts_raw (B,) i32."""
+    lib = load()
+    pred_cls = _contig(pred_cls, "pred_cls", torch.float32, 4)
+    pred_box = _contig(pred_box, "pred_box", torch.float32, 4)
+    B, c4, H, W = pred_cls.shape
+    if c4 != 4 or tuple(pred_box.shape) != (B, 14, H, W):
+        raise ValueError("get_bboxes: expected (B,4,H,W) and (B,14,H,W)")
+    boxes = torch.zeros((B, cap, 7), dtype=torch.float32, device=pred_cls.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=pred_cls.device)
+    raw = torch.empty((B,), dtype=torch.int32, device=pred_cls.device)
+    check(lib.cf_get_bboxes(ptr(pred_cls), ptr(pred_box), B, H, W, float(thr), cap, ptr(boxes), ptr(counts), ptr(raw),
+                            stream_ptr()), "cf_get_bboxes")
+    return boxes, counts, raw
+
+
+def _nms(fn_name, boxes, counts, extra=()):
+    lib = load()
+    boxes = _contig(boxes, "boxes", torch.float32, 3)
+    counts = _contig(counts, "counts", torch.int32, 1)
+    B, cap, seven = boxes.shape
+    if seven != 7 or counts.shape[0] != B:
+        raise ValueError("nms: expected boxes (B,cap,7) and counts (B,)")
+    keep = torch.empty((B, cap), dtype=torch.int32, device=boxes.device)
+    kcnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    ws = torch.empty((max(lib.cf_nms_workspace_bytes(B, cap), 16),), dtype=torch.uint8, device=boxes.device)
+    fn = getattr(lib, fn_name)
+    check(fn(ptr(boxes), ptr(counts), B, cap, *extra, ptr(keep), ptr(kcnt), ptr(ws), stream_ptr()), fn_name)
+    return keep, kcnt
+
+
+def nms_sat(boxes, counts):
+    """P-2..P-4.  boxes (B,cap,7), counts (B,) i32 -> keep_idx (B,cap) i32 (-1 padded), keep_count (B,) i32."""
+    return _nms("cf_nms_sat", boxes, counts)
+
+
+def nms_iou(boxes, counts, thr=0.01):
+    """P-7."""
+    return _nms("cf_nms_iou", boxes, counts, (float(thr),))
+
+
+def sat_matrix(boxes):
+    lib = load()
+    boxes = _contig(boxes, "boxes", torch.float32, 2)
+    n = boxes.shape[0]
+    m = torch.empty((n, n), dtype=torch.uint8, device=boxes.device)
+    check(lib.cf_sat_matrix(ptr(boxes), n, ptr(m), stream_ptr()), "cf_sat_matrix")
+    return m
+
+
+def box_iou(boxes_a, boxes_b, nudge_b=0.0):
+    """P-5/P-6.  (na,7), (nb,7) -> iou3d, iou2d (na,nb) float64."""
+    lib = load()
+    boxes_a = _contig(boxes_a, "boxes_a", torch.float32, 2)
+    boxes_b = _contig(boxes_b, "boxes_b", torch.float32, 2)
+    na, nb = boxes_a.shape[0], boxes_b.shape[0]
+    i3 = torch.empty((na, nb), dtype=torch.float64, device=boxes_a.device)
+    i2 = torch.empty((na, nb), dtype=torch.float64, device=boxes_a.device)
+    if na and nb:
+        check(lib.cf_box_iou(ptr(boxes_a), na, ptr(boxes_b), nb, float(nudge_b), ptr(i3), ptr(i2), stream_ptr()),
+              "cf_box_iou")
+    return i3, i2

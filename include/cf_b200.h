@@ -1,0 +1,156 @@
+/*
+ * cf_b200.h -- C ABI of libcf_b200.so: the B200 (sm_100a) continuous-fusion hot path and the
+ * rotated-box post-process, as bound by the Python host layer (ctypes) or any other FFI.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch's caching allocator);
+ *     kernels never allocate or free.  Workspaces are caller-provided, sized by cf_*_workspace_bytes.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     calls only enqueue work, they never synchronise.
+ *   - return value: 0 = CF_OK, negative = error class; cf_last_error() gives the thread-local text.
+ *   - a device that is not compute capability 10.x is a hard error (CF_ERR_ARCH): there is no fallback.
+ *   - tensors are dense row-major fp32 unless a stride argument says otherwise.
+ *
+ * Each entry point cites the reference interface it stands behind (file:line in the upstream tree)
+ * or, for the fusion layer the reference leaves as a TODO (model.py:199-203), the slot it fills.
+ */
+#ifndef CF_B200_H
+#define CF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CF_API __attribute__((visibility("default")))
+#else
+#define CF_API
+#endif
+
+#define CF_ABI_VERSION 1
+
+#define CF_OK 0
+#define CF_ERR_ARG (-1)         /* bad shape / null pointer / unsupported size */
+#define CF_ERR_ALIGN (-2)       /* pointer not aligned as documented            */
+#define CF_ERR_ARCH (-3)        /* no CUDA device, or device is not sm_100       */
+#define CF_ERR_LAUNCH (-4)      /* CUDA launch / runtime error                   */
+#define CF_ERR_UNSUPPORTED (-5) /* valid request this build does not implement   */
+
+#define CF_MAX_K 16 /* neighbours per BEV cell */
+
+/* MLP arithmetic of cf_fusion_fwd */
+#define CF_MODE_FP32 0      /* fp32-accurate: split-bf16 x3 on tcgen05 (or FFMA), fp32 accumulate */
+#define CF_MODE_BF16 1      /* bf16 operands on tcgen05, fp32 accumulate / pool / add            */
+#define CF_MODE_FP32_SIMT 2 /* CUDA-core FFMA path (bring-up / cross-check path)                  */
+
+CF_API int cf_abi_version(void);
+CF_API const char *cf_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x). */
+CF_API int cf_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-1  point bucketing: counting sort of the valid LiDAR points of each frame into a uniform BEV
+ * grid (histogram -> warp-scan exclusive prefix -> scatter).  Once per frame, shared by all scales.
+ *   d_points      (B,N,3) fp32, sample["pointcloud_raw"]   data_import_carla.py:263-264,71,79
+ *   d_num_points  (B) int64,   sample["num_points_raw"]    data_import_carla.py:262,73,81 (collated)
+ *   grid: bucket (bx,by) covers [gx0+bx*cell, +cell) x [gy0+by*cell, +cell); points outside are
+ *         clamped into the border buckets.
+ *   d_bucket_start (B, nbx*nby+1) int32 out; d_sorted (B,N,4) fp32 out = (x, y, z, bits(idx)).
+ *   d_workspace    cf_bucket_workspace_bytes(B, nbx, nby) bytes.
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_bucket_workspace_bytes(int32_t B, int32_t nbx, int32_t nby);
+CF_API int cf_bucket_points(const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N, float gx0,
+                     float gy0, float cell, int32_t nbx, int32_t nby, int32_t *d_bucket_start,
+                     float *d_sorted, void *d_workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-2  bounded-radius top-K query per BEV cell.  Fills the KNN half of the
+ * TODO at model.py:199-203 for the feature map produced at model.py:74-78.
+ *   cell (i,j) centre: cx = x0 + (float)i*dx, cy = y0 + (float)j*dy (fp32, separately rounded);
+ *   d2 = (px-cx)^2 + (py-cy)^2 fp32 without FMA; keep d2 <= radius*radius; ascending (d2, idx).
+ *   d_knn_idx (B,H,W,K) int32 out, -1 = empty slot.  1 <= K <= CF_MAX_K.
+ * ------------------------------------------------------------------------------------------- */
+CF_API int cf_knn_query(const int32_t *d_bucket_start, const float *d_sorted, int32_t B, int32_t N, float gx0,
+                 float gy0, float cell, int32_t nbx, int32_t nby, int32_t H, int32_t W, float x0, float y0,
+                 float dx, float dy, float radius, int32_t K, int32_t *d_knn_idx, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-3  projection + bilinear gather, once per frame (Appendix A6, A7).
+ *   d_img_feat  camera feature map, logical (B,Ci,Hf,Wf) fp32 with ELEMENT strides sb,sc,sh,sw
+ *               (NCHW contiguous or channels_last both accepted; Ci % 4 == 0)
+ *   uv source   exactly one of: d_uv (B,N,2) = sample["projected_loc_uv"], data_import_carla.py:265-266;
+ *               or h_calib, 12 HOST floats = CRT_tensor (4,3), data_import_carla.py:31-34,199-200
+ *   d_feat      (B,N,Ci) fp32 out; rows >= num_points[b] are left untouched
+ *   d_workspace cf_gather_workspace_bytes(...) bytes (pixel-major copy of the map when sc != 1)
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_gather_workspace_bytes(int32_t B, int32_t Ci, int32_t Hf, int32_t Wf, int64_t sc);
+CF_API int cf_point_gather(const float *d_img_feat, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B,
+                    int32_t Ci, int32_t Hf, int32_t Wf, const float *d_points, const float *d_uv,
+                    const float *h_calib, const int64_t *d_num_points, int32_t N, float img_w, float img_h,
+                    float *d_feat, void *d_workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-4a per-point half of MLP layer 1 (exact factorisation of Appendix A8/A9):
+ *   T[b,p,:] = W1[:, :Ci] f_p + W1[:, Ci:Ci+3] (px,py,pz) + b1        so that for BEV cell centre c
+ *   relu(W1 [f_p, p - (cx,cy,0)] + b1) = relu(T[b,p,:] - W1[:,Ci]*cx - W1[:,Ci+1]*cy)
+ *   d_W1 (C, Ci+3) fp32 row-major (nn.Linear.weight layout), d_b1 (C).  d_T (B,N,C) fp32 out.
+ * ------------------------------------------------------------------------------------------- */
+CF_API int cf_point_mlp1(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
+                  int32_t N, int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-4  per-neighbour MLP layers 1b/2/3 + K-sum-pool + BEV add for one scale (Appendix A9, A10);
+ * the result replaces `x` after a residual group in ResnetCustomed.forward (model.py:74-78).
+ *   out[b,:,i,j] = bev[b,:,i,j] + W3 * sum_k relu(W2 relu(T[b,idx_k,:] - e_ij) + b2) + n_valid*b3
+ *   d_bev/d_out (B,C,H,W) fp32 NCHW contiguous (may alias); C % 16 == 0, 16 <= C <= 256.
+ *   mode: CF_MODE_*.   d_workspace: cf_fusion_workspace_bytes(C, mode) bytes (packed weights).
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode);
+CF_API int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_knn_idx, int32_t B, int32_t N,
+                  int32_t C, int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
+                  const float *d_W1, int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3,
+                  const float *d_b3, float *d_out, int32_t mode, void *d_workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P-1  Test.get_bboxes (test.py:88-108) on device: per frame, anchor 0 then anchor 1, cells in
+ * row-major order with cls[b,2a+1] > thr; gathers the 7 decoded channels [7a,7a+7).
+ *   d_pred_cls (B,4,H,W), d_pred_box (B,14,H,W) fp32; d_boxes (B,cap,7) out; d_counts (B) int32 out
+ *   (counts are clamped to cap; d_counts_raw, if non-null, receives the unclamped totals).
+ * ------------------------------------------------------------------------------------------- */
+CF_API int cf_get_bboxes(const float *d_pred_cls, const float *d_pred_box, int32_t B, int32_t H, int32_t W,
+                  float thr, int32_t cap, float *d_boxes, int32_t *d_counts, int32_t *d_counts_raw,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P-2..P-4  Test.NMS_SAT (test.py:142-175) with get_vertice_rect / separating_axis_theorem
+ * (separation_axis_theorem.py:82-94, 66-80): greedy in input order, box i is kept iff it overlaps no
+ * previously kept box.  fp32 arithmetic mirrors the reference under numpy >= 2.
+ *   d_boxes (B,cap,7) fp32 [x,y,z,l,w,h,yaw]; d_counts (B) int32
+ *   d_keep_idx (B,cap) int32 out, ascending kept input indices, -1 padded; d_keep_count (B) int32 out
+ *   d_workspace cf_nms_workspace_bytes(B,cap) bytes.
+ * P-7  Test.NMS_IOU (test.py:110-140): same rule with predicate iou3d > thr (kept box nudged +1e-4).
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_nms_workspace_bytes(int32_t B, int32_t cap);
+CF_API int cf_nms_sat(const float *d_boxes, const int32_t *d_counts, int32_t B, int32_t cap, int32_t *d_keep_idx,
+               int32_t *d_keep_count, void *d_workspace, void *stream);
+CF_API int cf_nms_iou(const float *d_boxes, const int32_t *d_counts, int32_t B, int32_t cap, float thr,
+               int32_t *d_keep_idx, int32_t *d_keep_count, void *d_workspace, void *stream);
+/* the (cap x cap) overlap predicate of one frame as a dense uint8 matrix, for mask-level parity tests */
+CF_API int cf_sat_matrix(const float *d_boxes, int32_t n, uint8_t *d_matrix, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P-5/P-6  get_3d_box + box3d_iou (IOU.py:127-155, 91-120) for every pair (a_i, b_j), with the
+ * reference's axis convention (rotation about axis 1; BEV polygon on axes (0,2); height on axis 1).
+ *   d_boxes_a (na,7), d_boxes_b (nb,7) fp32; d_iou3d, d_iou2d (na,nb) fp64 out; nudge_b as test.py:129.
+ * ------------------------------------------------------------------------------------------- */
+CF_API int cf_box_iou(const float *d_boxes_a, int32_t na, const float *d_boxes_b, int32_t nb, float nudge_b,
+               double *d_iou3d, double *d_iou2d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CF_B200_H */

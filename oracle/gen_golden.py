@@ -1,0 +1,137 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference through
+oracle/ref_shims.py) on seeded inputs.  Run in the build container only:
+
+    python oracle/gen_golden.py
+
+Each fixture stores the inputs and the reference's outputs; tests compare the CPU oracle (CPU suite) and
+the CUDA path (GPU suite) against them.  numpy 2.3.5 / torch 2.11 / scipy 1.18.1 (the reference's
+SAT arithmetic depends on numpy >= 2 scalar promotion).
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[0] = ROOT  # replace the script directory so that `oracle` is the package, not oracle.py
+from oracle import ref_shims as R  # noqa: E402
+import dcf_b200  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def car_boxes(rng, n, x=(0, 70), y=(-30, 30), z=(-2.0, -1.0)):
+    c = np.stack([rng.uniform(*x, n), rng.uniform(*y, n), rng.uniform(*z, n)], axis=1)
+    s = np.array([4.0, 2.0, 1.5]) * np.exp(0.1 * rng.normal(size=(n, 3)))
+    yaw = rng.uniform(-math.pi, math.pi, (n, 1))
+    return np.concatenate([c, s, yaw], axis=1).astype(np.float32)
+
+
+def edge_case_boxes():
+    b = [
+        [10, 0, -1, 4, 2, 1.5, 0.0],
+        [14, 0, -1, 4, 2, 1.5, 0.0],          # shares an edge with box 0 (closed-interval SAT -> overlap)
+        [18.0001, 0, -1, 4, 2, 1.5, 0.0],     # 1e-4 gap from box 1 -> separate
+        [10, 0, -1, 4, 2, 1.5, 0.0],          # identical to box 0
+        [30, 5, -1, 4, 2, 1.5, math.pi / 4],
+        [30, 5, -1, 2, 1, 1.0, math.pi / 4],  # nested in box 4
+        [32.5, 7.5, -1, 4, 2, 1.5, -math.pi / 4],  # corner region of box 4
+        [50, -10, -1, 4, 2, 1.5, math.pi / 2],
+        [50, -7, -1, 4, 2, 1.5, 0.0],         # T-junction touching box 7
+        [60, 20, -1, 4, 2, 1.5, 3.0],
+        [0.5, -29.5, -1, 4, 2, 1.5, 1.0],
+    ]
+    return np.array(b, dtype=np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = R.load()
+    # ---- NMS_SAT keep lists (test.py:142-175)
+    frames = {}
+    for n in (0, 1, 2, 50, 200, 600, 2000):
+        frames[f"uniform_{n}"] = dcf_b200.synthetic.nms_boxes(n, n) if n else np.zeros((0, 7), np.float32)
+    rng = np.random.default_rng(11)
+    frames["dense_300"] = car_boxes(rng, 300, x=(10, 30), y=(-8, 8))   # heavy overlap
+    frames["edge_cases"] = edge_case_boxes()
+    data = {}
+    for name, boxes in frames.items():
+        keep = R.nms_sat([torch.from_numpy(boxes)])[0]
+        data[f"{name}__boxes"] = boxes
+        data[f"{name}__keep"] = keep
+        print("nms_sat", name, boxes.shape[0], "->", len(keep))
+    np.savez_compressed(os.path.join(OUT, "nms_sat.npz"), **data)
+
+    # ---- pairwise SAT on the edge cases + a random set (separation_axis_theorem.py:66-94)
+    boxes = np.concatenate([edge_case_boxes(), car_boxes(np.random.default_rng(12), 53, x=(5, 40), y=(-10, 10))])
+    n = boxes.shape[0]
+    m = np.zeros((n, n), np.uint8)
+    verts = []
+    for i in range(n):
+        t = torch.from_numpy(boxes[i])
+        verts.append(ref.sat.get_vertice_rect(t[:3].numpy(), t[3:6].numpy(), t[6].numpy()))
+    for i in range(n):
+        for j in range(n):
+            m[i, j] = ref.sat.separating_axis_theorem(verts[i], verts[j])
+    np.savez_compressed(os.path.join(OUT, "sat_pairs.npz"), boxes=boxes, overlap=m,
+                        vertices=np.array(verts, dtype=np.float32))
+    print("sat_pairs", n, int(m.sum()))
+
+    # ---- rotated IoU (IOU.py:91-155 as called from test.py:185-196)
+    rng = np.random.default_rng(13)
+    a = np.concatenate([edge_case_boxes(), car_boxes(rng, 40, x=(0, 12), y=(-1, 1), z=(-6, 6))])
+    b = np.concatenate([edge_case_boxes()[::-1].copy(), car_boxes(rng, 40, x=(0, 12), y=(-1, 1), z=(-6, 6))])
+    i3 = np.zeros((a.shape[0], b.shape[0]))
+    i2 = np.zeros_like(i3)
+    bad = np.zeros(i3.shape, np.uint8)
+    for i in range(a.shape[0]):
+        ta = torch.from_numpy(a[i])
+        ca = ref.IOU.get_3d_box(ta[:3].numpy(), ta[3:6].numpy(), ta[6].numpy())
+        for j in range(b.shape[0]):
+            tb = torch.from_numpy(b[j])
+            cb = ref.IOU.get_3d_box(tb[:3].numpy(), tb[3:6].numpy(), tb[6].numpy())
+            try:
+                i3[i, j], i2[i, j] = ref.IOU.box3d_iou(ca, cb)
+            except Exception:  # Qhull refuses degenerate clip polygons; the reference would crash here
+                bad[i, j] = 1
+    np.savez_compressed(os.path.join(OUT, "box_iou.npz"), boxes_a=a, boxes_b=b, iou3d=i3, iou2d=i2, qhull_error=bad)
+    print("box_iou", i3.shape, "overlapping pairs", int((i2 > 0).sum()), "qhull errors", int(bad.sum()))
+    # known answer of IOU.py:161-168 with its float64 corners
+    c1 = ref.IOU.get_3d_box((2.882992, 1.698800, 20.785644), (1.497255, 1.644981, 3.628938), -1.531692)
+    c2 = ref.IOU.get_3d_box((2.756923, 1.661275, 20.943280), (1.458242, 1.604773, 3.707947), -1.549553)
+    ka = ref.IOU.box3d_iou(c2, c1)
+    np.savez_compressed(os.path.join(OUT, "box_iou_known.npz"), corners_pred=c2, corners_gt=c1, iou=np.array(ka))
+    print("known answer", ka)
+
+    # ---- NMS_IOU (test.py:110-140)
+    bx = car_boxes(np.random.default_rng(14), 120, x=(0, 40), y=(-1, 1), z=(-15, 15))
+    keep = R.nms_iou([torch.from_numpy(bx)], 0.01)[0]
+    np.savez_compressed(os.path.join(OUT, "nms_iou.npz"), boxes=bx, keep=keep, thr=np.float32(0.01))
+    print("nms_iou", bx.shape[0], "->", len(keep))
+
+    # ---- get_bboxes (test.py:88-108)
+    g = torch.Generator().manual_seed(15)
+    cls = torch.rand(3, 4, 24, 16, generator=g)
+    box = torch.randn(3, 14, 24, 16, generator=g)
+    out = R.get_bboxes(cls, box, 0.8)
+    np.savez_compressed(os.path.join(OUT, "get_bboxes.npz"), cls=cls.numpy(), box=box.numpy(), thr=np.float32(0.8),
+                        counts=np.array([o.shape[0] for o in out]), boxes=torch.cat(out).numpy())
+    print("get_bboxes", [o.shape[0] for o in out])
+
+    # ---- dataset-side projection / filter / padding (data_import_carla.py:196-267) on synthetic returns
+    cfg = dcf_b200.geometry.carla_config()
+    ds = R.carla_dataset_stub(cfg)
+    raw = dcf_b200.synthetic.lidar_sweep(np.random.default_rng(16), 32, 700)
+    _, pc, uv, num, _ = ds.Voxelization_Projection(torch.from_numpy(raw))
+    np.savez_compressed(os.path.join(OUT, "projection.npz"), raw=raw, pointcloud_raw=pc.numpy()[:num + 8],
+                        projected_loc_uv=uv.numpy()[:num + 8], num_points_raw=np.int64(num),
+                        crt=ds.CRT_tensor.numpy())
+    print("projection", raw.shape[0], "->", num)
+
+
+if __name__ == "__main__":
+    main()

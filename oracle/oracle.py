@@ -1,0 +1,243 @@
+"""ctypes front-end of the CPU oracle (oracle/cf_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this module; the product package never does (its ops raise if the CUDA library is missing).
+
+All functions take / return numpy arrays.  Semantics and reference citations are in cf_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcf_oracle.so")
+_lib = None
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc, seconds)."""
+    src = os.path.join(_HERE, "cf_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libcf_oracle.so"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.cfo_knn_bruteforce.argtypes = [_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                         C.c_float, C.c_float, C.c_float, C.c_int32, _i32p, C.c_int64, C.c_int64]
+        L.cfo_project_points.argtypes = [_f32p, C.c_int32, _f32p, _f32p]
+        L.cfo_gather_points.argtypes = [_f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_float,
+                                        C.c_float, _f32p]
+        L.cfo_fusion_mlp.argtypes = [_f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_int32, _f32p, _i32p,
+                                     C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _f32p, _f32p, _f32p,
+                                     _f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_int64]
+        L.cfo_get_vertice_rect.argtypes = [_f32p, _f32p]
+        L.cfo_sat_axes.argtypes = [_f32p, _f32p]
+        L.cfo_set_sq_mode.argtypes = [C.c_int]
+        L.cfo_sat_overlap.argtypes = [_f32p, _f32p]
+        L.cfo_sat_overlap.restype = C.c_int
+        L.cfo_sat_polygons.argtypes = [_f32p, C.c_int32, _f32p, C.c_int32]
+        L.cfo_sat_polygons.restype = C.c_int
+        L.cfo_nms_sat.argtypes = [_f32p, C.c_int32, _i32p]
+        L.cfo_nms_sat.restype = C.c_int32
+        L.cfo_sat_matrix.argtypes = [_f32p, C.c_int32, _u8p]
+        L.cfo_get_3d_box.argtypes = [_f32p, _f64p]
+        L.cfo_box3d_iou.argtypes = [_f32p, _f32p, C.c_float, _f64p, _f64p]
+        L.cfo_box3d_iou_corners.argtypes = [_f64p, _f64p, _f64p, _f64p]
+        L.cfo_box3d_iou_matrix.argtypes = [_f32p, C.c_int32, _f32p, C.c_int32, C.c_float, _f64p, _f64p]
+        L.cfo_nms_iou.argtypes = [_f32p, C.c_int32, C.c_float, _i32p]
+        L.cfo_nms_iou.restype = C.c_int32
+        L.cfo_get_bboxes.argtypes = [_f32p, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p]
+        L.cfo_get_bboxes.restype = C.c_int32
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+# ------------------------------------------------------------------------------------------ fusion
+def knn_bruteforce(pts, n_valid, H, W, x0, y0, dx, dy, r2, K, cell_range=None):
+    """(H*W or range, K) int32 indices, -1 = empty slot.  One frame."""
+    pts = _f32(pts)
+    b, e = (0, H * W) if cell_range is None else cell_range
+    out = np.empty((e - b, K), dtype=np.int32)
+    lib().cfo_knn_bruteforce(_p(pts, _f32p), int(n_valid), H, W, np.float32(x0), np.float32(y0), np.float32(dx),
+                             np.float32(dy), np.float32(r2), K, _p(out, _i32p), b, e)
+    return out if cell_range is not None else out.reshape(H, W, K)
+
+
+def project_points(pts, calib):
+    pts = _f32(pts)
+    calib = _f32(calib)
+    assert calib.shape == (4, 3)
+    uv = np.empty((pts.shape[0], 2), dtype=np.float32)
+    lib().cfo_project_points(_p(pts, _f32p), pts.shape[0], _p(calib, _f32p), _p(uv, _f32p))
+    return uv
+
+
+def gather_points(img, uv, img_w=640.0, img_h=480.0):
+    """img (Ci,Hf,Wf), uv (n,2) -> (n,Ci)."""
+    img = _f32(img)
+    uv = _f32(uv)
+    Ci, Hf, Wf = img.shape
+    out = np.empty((uv.shape[0], Ci), dtype=np.float32)
+    lib().cfo_gather_points(_p(img, _f32p), Ci, Hf, Wf, _p(uv, _f32p), uv.shape[0], img_w, img_h, _p(out, _f32p))
+    return out
+
+
+def fusion_mlp(bev, feat, pts, knn, geom, weights, cell_range=None):
+    """bev (C,H,W); feat (n,Ci); pts (N,3); knn (H,W,K); geom=(x0,y0,dx,dy); weights=(W1,b1,W2,b2,W3,b3)."""
+    bev = _f32(bev)
+    Cc, H, W = bev.shape
+    feat = _f32(feat)
+    pts = _f32(pts)
+    knn = np.ascontiguousarray(knn, dtype=np.int32)
+    K = knn.shape[-1]
+    W1, b1, W2, b2, W3, b3 = [_f32(w) for w in weights]
+    Ci = feat.shape[1]
+    assert W1.shape == (Cc, Ci + 3) and W2.shape == (Cc, Cc) and W3.shape == (Cc, Cc)
+    x0, y0, dx, dy = [np.float32(g) for g in geom]
+    if cell_range is None:
+        out = np.empty_like(bev)
+        lib().cfo_fusion_mlp(_p(bev, _f32p), Cc, H, W, _p(feat, _f32p), Ci, _p(pts, _f32p), _p(knn, _i32p), K, x0, y0,
+                             dx, dy, _p(W1, _f32p), _p(b1, _f32p), _p(W2, _f32p), _p(b2, _f32p), _p(W3, _f32p),
+                             _p(b3, _f32p), _p(out, _f32p), 0, H * W)
+        return out
+    # bounded sample (bench cpu_baseline): knn is (range,K); output written into a full-size buffer
+    b, e = cell_range
+    out = np.zeros_like(bev)
+    lib().cfo_fusion_mlp(_p(bev, _f32p), Cc, H, W, _p(feat, _f32p), Ci, _p(pts, _f32p), _p(knn, _i32p), K, x0, y0, dx,
+                         dy, _p(W1, _f32p), _p(b1, _f32p), _p(W2, _f32p), _p(b2, _f32p), _p(W3, _f32p), _p(b3, _f32p),
+                         _p(out, _f32p), b, e)
+    return out
+
+
+def fusion_forward(bev, img, pts, n_valid, geom, radius, K, weights, calib=None, uv=None, img_w=640.0, img_h=480.0,
+                   return_knn=False):
+    """One frame, one scale, the whole layer: KNN -> projection -> gather -> MLP -> pool -> add."""
+    bev = _f32(bev)
+    _, H, W = bev.shape
+    pts = _f32(pts)
+    x0, y0, dx, dy = geom
+    r2 = np.float32(radius) * np.float32(radius)
+    knn = knn_bruteforce(pts, n_valid, H, W, x0, y0, dx, dy, r2, K)
+    if uv is None:
+        uv = project_points(pts[:n_valid], calib)
+    feat = gather_points(img, _f32(uv)[:n_valid], img_w, img_h)
+    out = fusion_mlp(bev, feat, pts, knn, geom, weights)
+    return (out, knn) if return_knn else out
+
+
+# ------------------------------------------------------------------------------------ post-process
+def get_vertice_rect(box7):
+    b = _f32(box7)
+    o = np.empty(8, dtype=np.float32)
+    lib().cfo_get_vertice_rect(_p(b, _f32p), _p(o, _f32p))
+    return o.reshape(4, 2)
+
+
+def sat_axes(box7):
+    b = _f32(box7)
+    o = np.empty(8, dtype=np.float32)
+    lib().cfo_sat_axes(_p(b, _f32p), _p(o, _f32p))
+    return o.reshape(4, 2)
+
+
+def set_sq_mode(m: int):
+    lib().cfo_set_sq_mode(int(m))
+
+
+def sat_overlap(box_a, box_b) -> bool:
+    a, b = _f32(box_a), _f32(box_b)
+    return bool(lib().cfo_sat_overlap(_p(a, _f32p), _p(b, _f32p)))
+
+
+def sat_polygons(va, vb) -> bool:
+    """separating_axis_theorem on two convex polygons given as (n,2) vertex arrays."""
+    a, b = _f32(va).reshape(-1, 2), _f32(vb).reshape(-1, 2)
+    return bool(lib().cfo_sat_polygons(_p(a, _f32p), a.shape[0], _p(b, _f32p), b.shape[0]))
+
+
+def nms_sat(boxes):
+    """(n,7) -> ascending kept input indices (int32)."""
+    boxes = _f32(boxes).reshape(-1, 7)
+    keep = np.empty(max(boxes.shape[0], 1), dtype=np.int32)
+    n = lib().cfo_nms_sat(_p(boxes, _f32p), boxes.shape[0], _p(keep, _i32p))
+    return keep[:n].copy()
+
+
+def sat_matrix(boxes):
+    boxes = _f32(boxes).reshape(-1, 7)
+    n = boxes.shape[0]
+    m = np.empty((n, n), dtype=np.uint8)
+    lib().cfo_sat_matrix(_p(boxes, _f32p), n, _p(m, _u8p))
+    return m
+
+
+def get_3d_box(box7):
+    b = _f32(box7)
+    o = np.empty(24, dtype=np.float64)
+    lib().cfo_get_3d_box(_p(b, _f32p), _p(o, _f64p))
+    return o.reshape(8, 3)
+
+
+def box3d_iou(box_a, box_b, nudge_b=0.0):
+    a, b = _f32(box_a), _f32(box_b)
+    i3, i2 = C.c_double(), C.c_double()
+    lib().cfo_box3d_iou(_p(a, _f32p), _p(b, _f32p), np.float32(nudge_b), C.byref(i3), C.byref(i2))
+    return i3.value, i2.value
+
+
+def box3d_iou_corners(c1, c2):
+    """IOU.box3d_iou on two (8,3) float64 corner arrays."""
+    c1 = np.ascontiguousarray(c1, dtype=np.float64)
+    c2 = np.ascontiguousarray(c2, dtype=np.float64)
+    i3, i2 = C.c_double(), C.c_double()
+    lib().cfo_box3d_iou_corners(_p(c1, _f64p), _p(c2, _f64p), C.byref(i3), C.byref(i2))
+    return i3.value, i2.value
+
+
+def box3d_iou_matrix(boxes_a, boxes_b, nudge_b=0.0):
+    a = _f32(boxes_a).reshape(-1, 7)
+    b = _f32(boxes_b).reshape(-1, 7)
+    i3 = np.empty((a.shape[0], b.shape[0]), dtype=np.float64)
+    i2 = np.empty_like(i3)
+    lib().cfo_box3d_iou_matrix(_p(a, _f32p), a.shape[0], _p(b, _f32p), b.shape[0], np.float32(nudge_b),
+                               _p(i3, _f64p), _p(i2, _f64p))
+    return i3, i2
+
+
+def nms_iou(boxes, thr=0.01):
+    boxes = _f32(boxes).reshape(-1, 7)
+    keep = np.empty(max(boxes.shape[0], 1), dtype=np.int32)
+    n = lib().cfo_nms_iou(_p(boxes, _f32p), boxes.shape[0], np.float32(thr), _p(keep, _i32p))
+    return keep[:n].copy()
+
+
+def get_bboxes(cls4, box14, thr=0.8):
+    """One frame: cls (4,H,W), decoded boxes (14,H,W) -> (n,7) in anchor-major / row-major order."""
+    cls4 = _f32(cls4)
+    box14 = _f32(box14)
+    _, H, W = cls4.shape
+    out = np.empty((2 * H * W, 7), dtype=np.float32)
+    n = lib().cfo_get_bboxes(_p(cls4, _f32p), _p(box14, _f32p), H, W, np.float32(thr), _p(out, _f32p))
+    return out[:n].copy()

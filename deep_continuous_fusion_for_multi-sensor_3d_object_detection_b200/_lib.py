@@ -22,6 +22,7 @@ SIGNATURES = {
     "cf_abi_version": (C.c_int, []),
     "cf_last_error": (C.c_char_p, []),
     "cf_device_check": (C.c_int, []),
+    "cf_launch_count": (C.c_longlong, []),
     "cf_bucket_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "cf_bucket_points": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cf_knn_query": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32,

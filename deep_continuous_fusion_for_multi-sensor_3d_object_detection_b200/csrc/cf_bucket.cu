@@ -110,5 +110,6 @@ extern "C" int cf_bucket_points(const float *d_points, const int64_t *d_num_poin
     k_bucket_hist<<<dim3(blocks, B), 256, 0, st>>>(d_points, d_num_points, N, g, cursor);
     k_bucket_scan<<<B, 1024, 0, st>>>(cursor, G, d_bucket_start);
     k_bucket_scatter<<<dim3(blocks, B), 256, 0, st>>>(d_points, d_num_points, N, g, cursor, (float4 *)d_sorted);
+    count_launches(3);
     return launch_status("cf_bucket_points");
 }

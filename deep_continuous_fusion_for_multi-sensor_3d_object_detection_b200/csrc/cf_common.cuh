@@ -18,6 +18,8 @@ int launch_status(const char *what);
 // 0 when the current device is compute capability 10.x (cached per device)
 int require_sm100();
 int sm_count();
+// bookkeeping behind cf_launch_count(): every kernel launch of this library is counted
+void count_launches(int n);
 
 #define CF_REQUIRE(cond, code, ...)      \
     do {                                 \

@@ -139,6 +139,7 @@ extern "C" int cf_point_gather(const float *d_img_feat, int64_t sb, int64_t sc, 
         const int32_t HW = Hf * Wf;
         dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Ci + 31) / 32), (unsigned)B);
         k_to_pixel_major<<<grid, 256, 0, st>>>(d_img_feat, sb, sc, sh, sw, Ci, Hf, Wf, (float *)d_workspace);
+        count_launches(1);
         pix = (const float *)d_workspace;
         pb = (int64_t)HW * Ci;
         ph = (int64_t)Wf * Ci;
@@ -154,5 +155,6 @@ extern "C" int cf_point_gather(const float *d_img_feat, int64_t sb, int64_t sc, 
     const int blocks = (int)std::min<int64_t>(ceil_div64(N, 8), 148 * 16);
     k_point_gather<<<dim3(blocks, B), 256, 0, st>>>(pix, pb, ph, pw, Ci, Hf, Wf, d_points, d_uv, cal,
                                                     h_calib != nullptr, d_num_points, N, sx, sy, d_feat);
+    count_launches(1);
     return launch_status("cf_point_gather");
 }

@@ -164,5 +164,6 @@ extern "C" int cf_knn_query(const int32_t *d_bucket_start, const float *d_sorted
         CF_KNN_CASE(13) CF_KNN_CASE(14) CF_KNN_CASE(15) CF_KNN_CASE(16)
 #undef CF_KNN_CASE
     }
+    count_launches(1);
     return launch_status("cf_knn_query");
 }

@@ -214,6 +214,7 @@ int fusion_simt(const float *d_bev, const float *d_T, const int32_t *d_knn, int3
     const int gx = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 8);
     k_fusion_simt<<<dim3(gx, B), 256, smem, st>>>(d_bev, d_T, d_knn, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, Wt2,
                                                   d_b2, Wt3, d_b3, d_out);
+    count_launches(3);
     return launch_status("cf_fusion_fwd (simt)");
 }
 
@@ -231,5 +232,6 @@ extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const i
     CF_REQUIRE(aligned16(d_feat) && aligned16(d_T), CF_ERR_ALIGN, "cf_point_mlp1: feat/T must be 16-byte aligned");
     dim3 grid((unsigned)((N + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
     k_point_mlp1<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feat, d_points, d_num_points, N, Ci, C, d_W1, d_b1, d_T);
+    count_launches(1);
     return launch_status("cf_point_mlp1");
 }

@@ -260,6 +260,7 @@ extern "C" int cf_get_bboxes(const float *d_pred_cls, const float *d_pred_box, i
     CF_REQUIRE(B > 0 && H > 0 && W > 0 && cap > 0, CF_ERR_ARG, "cf_get_bboxes: bad extents");
     k_get_bboxes<<<B, 1024, 0, (cudaStream_t)stream>>>(d_pred_cls, d_pred_box, H, W, thr, cap, d_boxes, d_counts,
                                                        d_counts_raw);
+    count_launches(1);
     return launch_status("cf_get_bboxes");
 }
 
@@ -297,6 +298,7 @@ extern "C" int cf_nms_sat(const float *d_boxes, const int32_t *d_counts, int32_t
     k_sat_prepare<<<dim3((cap + 127) / 128, B), 128, 0, st>>>(d_boxes, d_counts, cap, prep);
     k_sat_mask<<<dim3(nw, nw, B), 64, 0, st>>>(prep, d_counts, cap, nw, mask);
     k_nms_scan<<<B, kNmsMaxWords, 0, st>>>(mask, d_counts, cap, nw, d_keep_idx, d_keep_count);
+    count_launches(3);
     return launch_status("cf_nms_sat");
 }
 
@@ -315,6 +317,7 @@ extern "C" int cf_nms_iou(const float *d_boxes, const int32_t *d_counts, int32_t
     k_iou_prepare<<<dim3((cap + 127) / 128, B), 128, 0, st>>>(d_boxes, d_counts, cap, 0.0001f, nudged);
     k_iou_mask<<<dim3(nw, nw, B), 64, 0, st>>>(plain, nudged, d_counts, cap, nw, (double)thr, mask);
     k_nms_scan<<<B, kNmsMaxWords, 0, st>>>(mask, d_counts, cap, nw, d_keep_idx, d_keep_count);
+    count_launches(4);
     return launch_status("cf_nms_iou");
 }
 
@@ -324,6 +327,7 @@ extern "C" int cf_sat_matrix(const float *d_boxes, int32_t n, uint8_t *d_matrix,
     CF_TRY(require_sm100());
     CF_REQUIRE(d_boxes && d_matrix && n > 0 && n <= 65535, CF_ERR_ARG, "cf_sat_matrix: bad arguments");
     k_sat_matrix<<<dim3((n + 127) / 128, n), 128, 0, (cudaStream_t)stream>>>(d_boxes, n, d_matrix);
+    count_launches(1);
     return launch_status("cf_sat_matrix");
 }
 
@@ -336,5 +340,6 @@ extern "C" int cf_box_iou(const float *d_boxes_a, int32_t na, const float *d_box
     CF_REQUIRE(na > 0 && nb > 0 && na <= 65535, CF_ERR_ARG, "cf_box_iou: bad extents");
     k_box_iou<<<dim3((nb + 127) / 128, na), 128, 0, (cudaStream_t)stream>>>(d_boxes_a, na, d_boxes_b, nb, nudge_b,
                                                                            d_iou3d, d_iou2d);
+    count_launches(1);
     return launch_status("cf_box_iou");
 }

@@ -1,5 +1,6 @@
 // cf_runtime.cu -- error channel, device checks (C ABI: cf_abi_version, cf_last_error, cf_device_check).
 #include <stdarg.h>
+#include <atomic>
 #include <stdio.h>
 
 #include "cf_common.cuh"
@@ -24,6 +25,9 @@ int cuda_status(cudaError_t err, const char *what)
 }
 
 int launch_status(const char *what) { return cuda_status(cudaGetLastError(), what); }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int g_arch_ok[64];  // 0 unknown, 1 ok, -1 bad
 static int g_sms[64];
@@ -70,4 +74,5 @@ extern "C" {
 int cf_abi_version(void) { return CF_ABI_VERSION; }
 const char *cf_last_error(void) { return cf::g_err; }
 int cf_device_check(void) { return cf::require_sm100(); }
+long long cf_launch_count(void) { return cf::g_launches.load(std::memory_order_relaxed); }
 }

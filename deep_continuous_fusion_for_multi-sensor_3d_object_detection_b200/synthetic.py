@@ -132,27 +132,28 @@ def nms_boxes(seed: int, n: int) -> np.ndarray:
 # workloads of BASELINE.json `configs`
 def workload(name: str) -> dict:
     if name == "cfg0":  # single CARLA-shaped frame, 700x800 BEV, K=3, one scale, batch 1
-        return dict(name=name, batch=1, bev=(700, 800), scales=(1,), k=3, max_num_pc=20000, n_beams=32, n_az=1900,
+        return dict(name=name, batch=1, bev=(700, 800), scales=(1,), k=3, max_num_pc=20000, n_beams=32, n_az=1500,
                     mode="fp32")
     if name == "cfg1":  # batch 4, K=5, every residual group, fp32
         return dict(name=name, batch=4, bev=(700, 800), scales=(1, 2, 3, 4, 5), k=5, max_num_pc=20000, n_beams=32,
-                    n_az=1900, mode="fp32")
+                    n_az=1500, mode="fp32")
     if name == "cfg2":  # 64-beam density, K=10, bf16 MLP, batch 8
         return dict(name=name, batch=8, bev=(700, 800), scales=(1, 2, 3, 4, 5), k=10, max_num_pc=131072, n_beams=64,
-                    n_az=5600, mode="bf16")
+                    n_az=4800, mode="bf16")
     if name == "yaml":  # the reference YAML's own 384x256 grid
         return dict(name=name, batch=2, bev=(384, 256), scales=(1, 2, 3, 4, 5), k=3, max_num_pc=20000, n_beams=32,
-                    n_az=1900, mode="fp32")
+                    n_az=1500, mode="fp32")
     if name == "tiny":
-        return dict(name=name, batch=2, bev=(48, 40), scales=(1, 2), k=3, max_num_pc=2048, n_beams=16, n_az=200,
-                    mode="fp32")
+        return dict(name=name, batch=2, bev=(96, 80), scales=(1, 2), k=3, max_num_pc=2048, n_beams=24, n_az=200,
+                    mode="fp32", lidar_range=dict(lidar_x_max=24.0, lidar_y_min=-10.0, lidar_y_max=10.0))
     raise KeyError(name)
 
 
 def make_workload(name_or_dict, seed: int = 0, c_img: int = 128, img_hw=(120, 160), channels=None):
     """All host-side numpy inputs of one fusion step: points, uv, counts, image map, BEV maps, weights."""
     wl = workload(name_or_dict) if isinstance(name_or_dict, str) else dict(name_or_dict)
-    cfg = G.carla_config(voxel_length=wl["bev"][0], voxel_width=wl["bev"][1], max_num_pc=wl["max_num_pc"])
+    cfg = G.carla_config(voxel_length=wl["bev"][0], voxel_width=wl["bev"][1], max_num_pc=wl["max_num_pc"],
+                         **wl.get("lidar_range", {}))
     B = wl["batch"]
     pts, uv, cnt = make_points(seed, cfg, wl["n_beams"], wl["n_az"], B, uniform=wl.get("uniform", False))
     rng = np.random.default_rng(9000 + seed)

@@ -50,6 +50,8 @@ CF_API int cf_abi_version(void);
 CF_API const char *cf_last_error(void);
 /* 0 if the current device can run this library (compute capability 10.x). */
 CF_API int cf_device_check(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+CF_API long long cf_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K-1  point bucketing: counting sort of the valid LiDAR points of each frame into a uniform BEV

@@ -1,0 +1,84 @@
+"""GPU: the whole fused layer (K-1..K-4) through ContinuousFusion / the C ABI against the brute-force,
+naive-formulation CPU oracle.  Tolerance (Appendix A13): ||out-ref||_inf / max(||ref||_inf, 1e-6) <= 1e-4 in
+fp32 modes, 1e-2 in bf16 mode; additionally the fusion DELTA (out - bev) must meet the same bound, so the
+N(0,1) BEV input cannot mask an error in the MLP."""
+import numpy as np
+import pytest
+import torch
+
+from _util import cuda_fusion, dev, oracle_fusion, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"simt": 1e-4, "fp32": 1e-4, "bf16": 1e-2}
+
+
+def _compare(wl, outs, knns, ref_outs, ref_knns, tol):
+    for sc, o, k, ro, rk in zip(wl["scales"], outs, knns, ref_outs, ref_knns):
+        assert np.array_equal(k, rk), f"group {sc['group']}: knn mismatch"
+        assert o.shape == ro.shape and o.dtype == np.float32
+        assert rel_err(o, ro) <= tol, f"group {sc['group']}: rel err {rel_err(o, ro):.3e}"
+        d, rd = o - sc["bev"], ro - sc["bev"]
+        assert np.abs(rd).max() > 1e-2                      # the layer actually contributes
+        assert rel_err(d, rd) <= tol * 2, f"group {sc['group']}: delta rel err {rel_err(d, rd):.3e}"
+
+
+@pytest.mark.parametrize("mode", ["simt", "fp32", "bf16"])
+@pytest.mark.parametrize("name,seed,use_uv", [("tiny", 11, False), ("tiny", 12, True)])
+def test_fusion_matches_oracle_small(dcf, oracle, mode, name, seed, use_uv):
+    wl = dcf.synthetic.make_workload(name, seed=seed, c_img=32, img_hw=(24, 32))
+    outs, knns = cuda_fusion(dcf, wl, mode, use_uv=use_uv)
+    ref_outs, ref_knns = oracle_fusion(oracle, wl, use_uv=use_uv)
+    _compare(wl, outs, knns, ref_outs, ref_knns, TOL[mode])
+
+
+@pytest.mark.parametrize("mode", ["simt", "fp32", "bf16"])
+def test_fusion_all_five_scales_yaml_grid(dcf, oracle, mode):
+    """The reference YAML's 384x256 grid, all five residual groups (C = 32..256), 128-channel camera map."""
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=1, k=5), seed=13)
+    outs, knns = cuda_fusion(dcf, wl, mode)
+    ref_outs, ref_knns = oracle_fusion(oracle, wl)
+    _compare(wl, outs, knns, ref_outs, ref_knns, TOL[mode])
+
+
+def test_fusion_channels_last_map_equals_nchw(dcf):
+    wl = dcf.synthetic.make_workload("tiny", seed=14, c_img=64, img_hw=(30, 40))
+    a, _ = cuda_fusion(dcf, wl, "simt", channels_last=False)
+    b, _ = cuda_fusion(dcf, wl, "simt", channels_last=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_fusion_empty_frame_is_identity(dcf):
+    """A frame with no points (or no point within the radius) must return bev unchanged (A4/A10)."""
+    wl = dcf.synthetic.make_workload("tiny", seed=15, c_img=32, img_hw=(24, 32))
+    wl["num_points"][:] = 0
+    for mode in ("simt", "fp32", "bf16"):
+        outs, knns = cuda_fusion(dcf, wl, mode)
+        for sc, o, k in zip(wl["scales"], outs, knns):
+            assert (k == -1).all()
+            assert np.array_equal(o, sc["bev"])
+
+
+def test_fusion_linearity_in_last_layer(dcf):
+    """Property (size independent): the layer is affine in (W3, b3): f(2*W3, 2*b3) - bev = 2 (f(W3,b3) - bev)."""
+    wl = dcf.synthetic.make_workload("tiny", seed=16, c_img=32, img_hw=(24, 32))
+    a, _ = cuda_fusion(dcf, wl, "fp32")
+    for sc in wl["scales"]:
+        w = list(sc["weights"])
+        w[4], w[5] = w[4] * 2, w[5] * 2
+        sc["weights"] = tuple(w)
+    b, _ = cuda_fusion(dcf, wl, "fp32")
+    for sc, x, y in zip(wl["scales"], a, b):
+        assert rel_err(y - sc["bev"], 2 * (x - sc["bev"])) < 1e-5
+
+
+def test_module_rejects_bad_inputs(dcf):
+    layer = dcf.ContinuousFusion(32, 32, geom=(0.0, 0.0, 1.0, 1.0)).cuda()
+    with pytest.raises(ValueError):
+        layer(torch.zeros(1, 16, 4, 4, device="cuda"), torch.zeros(1, 32, 4, 4, device="cuda"),
+              torch.zeros(1, 8, 3, device="cuda"), torch.tensor([3]))
+    with pytest.raises(ValueError):
+        dcf.ContinuousFusion(32, 40)
+    with pytest.raises(ValueError):
+        dcf.ContinuousFusion(32, 32, k=17)

@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- fusion-layer frames/s on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+A "step" is one pass of the continuous-fusion hot path over one batch of synthetic frames:
+K-1 bucket points, K-3 project + gather camera features, then per backbone scale K-4a per-point MLP half,
+K-2 KNN per BEV cell, K-4 fused MLP + K-sum-pool + BEV add.  Workload = BASELINE.json configs[1]
+(batch 4, K=5, fusion after every residual group, 700x800 BEV, fp32 parity mode) per GPU; frames are
+independent, so N GPUs run N disjoint batches with no collective on the data path (weak scaling).
+
+  value  frames/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e    same through the public nn.Module API with HOST buffers: pinned H2D of every input and D2H of every
+         fused BEV map inside the timed region
+  roofline      the dominant kernel against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (a port: the reference has no fusion layer to time) on a bounded sample
+
+`--impl reference` times that CPU port alone with all host threads (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fusion_layer_frames_per_sec"
+UNIT = "frames/s"
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def algorithmic_bytes_per_frame(wl, c_img, img_hw, n_valid_mean):
+    """sum_s [2*4*C_s*cells_s + 4*K*cells_s + weights_s] + 4*C_img*Hf*Wf + 12*n_b."""
+    K = wl["k"]
+    total = 4 * c_img * img_hw[0] * img_hw[1] + 12 * n_valid_mean
+    for sc in wl["scales"]:
+        cells = sc["H"] * sc["W"]
+        C = sc["C"]
+        total += 2 * 4 * C * cells + 4 * K * cells + 4 * (C * (c_img + 3) + 2 * C * C + 3 * C)
+    return float(total)
+
+
+def fusion_kernel_bytes(sc, B, K):
+    """Algorithmic bytes of ONE cf_fusion_fwd launch: BEV read + write, KNN indices read, layer weights."""
+    cells = sc["H"] * sc["W"]
+    C = sc["C"]
+    return float(B * (2 * 4 * C * cells + 4 * K * cells) + 4 * (2 * C * C + 4 * C))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU port
+def cpu_port_time(wl, budget_s=15.0, threads=None):
+    """Times the CPU oracle (brute-force KNN + gather + naive per-neighbour MLP) on a bounded sample of the
+    workload: frame 0, every scale, the first `f` of each scale's cells; returns (frames/s, description)."""
+    from oracle import oracle as O
+    threads = threads or os.cpu_count()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    O.build()
+    pts, n = wl["points"][0], int(wl["num_points"][0])
+    r2 = np.float32(wl["radius"]) ** 2
+    K = wl["k"]
+    uv = O.project_points(pts[:n], wl["calib"])
+    t0 = time.perf_counter()
+    feat = O.gather_points(wl["img_feat"][0], uv)
+    t_gather = time.perf_counter() - t0
+
+    def run(frac):
+        t = 0.0
+        for sc in wl["scales"]:
+            H, W = sc["H"], sc["W"]
+            cells = H * W
+            x0, y0, dx, dy = sc["geom"]
+            chunks = 8   # evenly spaced over the map, so near-ego (dense) and far (empty) cells are both sampled
+            m = max(1, int(cells * frac / chunks))
+            for c in range(chunks):
+                lo = min(cells - m, (cells // chunks) * c)
+                t0 = time.perf_counter()
+                knn = O.knn_bruteforce(pts, n, H, W, x0, y0, dx, dy, r2, K, cell_range=(lo, lo + m))
+                O.fusion_mlp(sc["bev"][0], feat, pts, knn, sc["geom"], sc["weights"], cell_range=(lo, lo + m))
+                t += time.perf_counter() - t0
+        return t
+
+    probe_frac = 0.002
+    run(probe_frac)            # warm the thread pool / page in
+    t_probe = run(probe_frac)
+    frac = float(min(1.0, max(probe_frac, probe_frac * budget_s / max(t_probe, 1e-3))))
+    t_sample = run(frac)
+    t_frame = t_gather + t_sample / frac
+    desc = (f"frame 0 of the workload, all {len(wl['scales'])} scales, {frac * 100:.2f}% of each scale's cells in 8 evenly spaced chunks "
+            f"({t_sample:.1f} s measured, extrapolated linearly to a frame) + full per-point gather")
+    return 1.0 / t_frame, desc, t_sample + t_gather + t_probe
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class GpuPipeline:
+    """Device-resident buffers + the op sequence of one step (through the package's public ops / modules)."""
+
+    def __init__(self, dcf, wl, mode, device):
+        import torch
+        self.torch, self.dcf, self.wl, self.mode = torch, dcf, wl, mode
+        self.device = device
+        self.grid = dcf.ops.BucketGrid(*dcf.geometry.bucket_grid(wl["config"]))
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.points, self.counts = dev(wl["points"]), dev(wl["num_points"])
+        self.img = dev(wl["img_feat"])
+        self.calib = wl["calib"]
+        self.layers, self.bev, self.out = [], [], []
+        c_img = self.img.shape[1]
+        for sc in wl["scales"]:
+            layer = dcf.ContinuousFusion(c_img, sc["C"], k=wl["k"], radius=wl["radius"], geom=sc["geom"], mode=mode).to(device)
+            with torch.no_grad():
+                for p, w in zip((layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
+                                 layer.fc3.bias), sc["weights"]):
+                    p.copy_(dev(w))
+            self.layers.append(layer.eval())
+            self.bev.append(dev(sc["bev"]))
+        self.size = (float(wl["config"]["image_width"]), float(wl["config"]["image_height"]))
+
+    def step(self, bev=None, points=None, counts=None, img=None):
+        torch = self.torch
+        bev = self.bev if bev is None else bev
+        with torch.no_grad():
+            frames = self.dcf.FrameContext(self.points if points is None else points,
+                                           self.counts if counts is None else counts, self.grid)
+            frames.gather(self.img if img is None else img, calib=self.calib, img_size=self.size)
+            return [layer(x, frames=frames) for layer, x in zip(self.layers, bev)]
+
+    def timed_ops(self):
+        """One step with a CUDA-event pair around every C-ABI call -> {op name: ms}, per-launch list."""
+        torch, ops = self.torch, self.dcf.ops
+        ev = []
+
+        def timed(name, fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            ev.append((name, a, b))
+            return r
+
+        with torch.no_grad():
+            start, srt, _ = timed("cf_bucket_points", lambda: ops.bucket_points(self.points, self.counts, self.grid))
+            feat, _ = timed("cf_point_gather", lambda: ops.point_gather(self.img, self.points, self.counts, calib=self.calib,
+                                                                        img_size=self.size))
+            for sc, layer, bev in zip(self.wl["scales"], self.layers, self.bev):
+                g = sc["group"]
+                T = timed(f"cf_point_mlp1[g{g}]", lambda: ops.point_mlp1(feat, self.points, self.counts, layer.fc1.weight,
+                                                                         layer.fc1.bias))
+                knn = timed(f"cf_knn_query[g{g}]", lambda: ops.knn_query(start, srt, self.grid, sc["H"], sc["W"], sc["geom"],
+                                                                         self.wl["radius"], self.wl["k"]))
+                timed(f"cf_fusion_fwd[g{g}]", lambda: ops.fusion_fwd(bev, T, knn, sc["geom"], layer.fc1.weight,
+                                                                     layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
+                                                                     layer.fc3.bias, mode=self.mode))
+        torch.cuda.synchronize()
+        return [(n, a.elapsed_time(b)) for n, a, b in ev]
+
+
+def run_gpu(args):
+    import torch
+    import dcf_b200 as dcf
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = dcf.synthetic.make_workload(args.workload, seed=100 + rank)   # disjoint frames per rank
+    B = wl["points"].shape[0]
+    mode = args.mode or wl["workload"]["mode"]
+    pipe = GpuPipeline(dcf, wl, mode, device)
+    lib = dcf.load()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        pipe.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.cf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        pipe.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.cf_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host buffers in, host buffers out ------------------------------------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_points, h_counts, h_img = pin(wl["points"]), pin(wl["num_points"]), pin(wl["img_feat"])
+    h_bev = [pin(sc["bev"]) for sc in wl["scales"]]
+    h_out = [torch.empty_like(b).pin_memory() for b in h_bev]
+    h2d = sum(t.numel() * t.element_size() for t in [h_points, h_counts, h_img] + h_bev)
+    d2h = sum(t.numel() * t.element_size() for t in h_out)
+
+    def e2e_step():
+        pts = h_points.to(device, non_blocking=True)
+        cnt = h_counts.to(device, non_blocking=True)
+        img = h_img.to(device, non_blocking=True)
+        bev = [b.to(device, non_blocking=True) for b in h_bev]
+        outs = pipe.step(bev=bev, points=pts, counts=cnt, img=img)
+        for o, h in zip(outs, h_out):
+            h.copy_(o, non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- max over ranks ---------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel times + roofline of the dominant kernel (rank 0) -------------------------------------
+    reps = 5
+    acc = {}
+    for _ in range(reps):
+        for name, t_ms in pipe.timed_ops():
+            acc.setdefault(name, []).append(t_ms)
+    per_op = {k: float(np.mean(v)) for k, v in acc.items()}
+    step_ms = ms / args.steps
+    dom = max(per_op, key=per_op.get)
+    peak, peak_src = measured_peaks()
+    K = wl["k"]
+    roof = None
+    if dom.startswith("cf_fusion_fwd"):
+        g = int(dom.split("[g")[1].rstrip("]"))
+        sc = [s for s in wl["scales"] if s["group"] == g][0]
+        nbytes = fusion_kernel_bytes(sc, B, K)
+        ach = nbytes / (per_op[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": nbytes, "ms_per_launch": round(per_op[dom], 4),
+                "share_of_step": round(per_op[dom] / sum(per_op.values()), 3)}
+    else:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src, "ms_per_launch": round(per_op[dom], 4),
+                "share_of_step": round(per_op[dom] / sum(per_op.values()), 3),
+                "note": "dominant kernel is compute/latency bound; see DESIGN.md"}
+    n_valid = float(np.mean(wl["num_points"]))
+    layer_bytes = algorithmic_bytes_per_frame(wl, wl["img_feat"].shape[1], wl["img_feat"].shape[2:], n_valid)
+    layer_gbs = layer_bytes * B / (step_ms * 1e-3) / 1e9
+
+    # ---- CPU port beside it ------------------------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, desc, _ = cpu_port_time(wl, budget_s=args.cpu_budget)
+        cpu = {"value": round(v, 6), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": round(B * world * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if mode in ("fp32", "simt") else "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: BASELINE.json configs[1] (batch {B}/GPU, K={K}, "
+                               f"{len(wl['scales'])} scales of a {wl['workload']['bev'][0]}x{wl['workload']['bev'][1]} BEV, "
+                               f"~{int(n_valid)} LiDAR points/frame, 128x120x160 camera map)",
+                   "mlp_mode": mode, "frames_per_step_per_gpu": B, "l2_policy": "inputs_exceed_l2 (BEV in+out "
+                   f"{2 * sum(b.numel() * 4 for b in pipe.bev) / 1e6:.0f} MB per step vs 126 MB L2)"},
+        "e2e": {"value": round(B * world * e2e_steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "layer": {"algorithmic_bytes_per_frame": layer_bytes, "achieved_gbs": round(layer_gbs, 1),
+                  "frac_of_hbm_peak": round(layer_gbs / peak, 4)},
+        "kernel_ms": {k: round(v, 4) for k, v in per_op.items()},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The CPU implementation of the same path on the host cores (rank 0 only).  The upstream repository has no
+    fusion layer (model.py:199-203 is a TODO), so the arm is the oracle PORT, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import dcf_b200 as dcf
+    wl = dcf.synthetic.make_workload(args.workload, seed=100)
+    B = wl["points"].shape[0]
+    steps = max(1, args.steps)
+    budget = min(args.cpu_budget, 120.0 / (steps + max(args.warmup, 0) + 1))
+    vals, desc = [], ""
+    for i in range(max(args.warmup, 0) + steps):
+        v, desc, _ = cpu_port_time(wl, budget_s=budget)
+        if i >= max(args.warmup, 0):
+            vals.append(v)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": max(args.warmup, 0),
+            "ms_per_step": round(1e3 * B / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: BASELINE.json configs[1]", "frames_per_step_per_gpu": B},
+            "cpu_baseline": {"value": round(v, 6), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc},
+            "e2e": {"value": round(v, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg1")
+    ap.add_argument("--mode", default=None, help="fp32 | bf16 | simt (default: the workload's)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

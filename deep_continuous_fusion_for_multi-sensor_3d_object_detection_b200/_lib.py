@@ -40,6 +40,7 @@ SIGNATURES = {
     "cf_nms_iou": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "cf_sat_matrix": (C.c_int, [_vp, _i32, _vp, _vp]),
     "cf_box_iou": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp]),
+    "cf_debug_umma_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
 }
 
 _lib = None

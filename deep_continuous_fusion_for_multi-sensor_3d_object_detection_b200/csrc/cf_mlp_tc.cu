@@ -1,17 +1,503 @@
-// cf_mlp_tc.cu -- tcgen05 version of K-4 (placeholder until the tensor-core kernel lands).
+// cf_mlp_tc.cu -- K-4 on the 5th-generation tensor cores: per-neighbour MLP layer 2, K-sum-pool, layer 3 and
+// the BEV add for one backbone scale, fused so that neither the gathered rows nor the hidden activations
+// ever leave the SM.
+//
+// Tile = 128 consecutive BEV cells (= the M of a cta_group::1 UMMA, one TMEM lane per cell).  Per tile:
+//   for each neighbour slot k:
+//     A_k[128 x C]  = relu(T[idx_k] - e_cell)            built by CUDA cores straight into shared memory in the
+//                                                         UMMA operand layout, bf16 (+ bf16 residual in fp32 mode)
+//     acc[128 x C]  = A_k * W2^T                          tcgen05.mma, accumulator in TMEM
+//     pooled       += valid ? relu(acc + b2) : 0          tcgen05.ld -> registers -> tcgen05.st (pooled lives in TMEM)
+//   acc = pooled * W3^T                                   tcgen05.mma
+//   out = bev + acc + n_valid * b3                        epilogue: coalesced NCHW read of bev, write of out
+// Slots for which no cell of the tile has a neighbour are skipped (most far-field tiles skip everything).
+//
+// Precision modes
+//   CF_MODE_BF16: operands rounded to bf16, fp32 accumulate (tolerance 1e-2, Appendix A12).
+//   CF_MODE_FP32: every fp32 operand x is split into bf16 hi + bf16 lo (x ~ hi + lo to 2^-17); the product is
+//                 hi*hi + hi*lo + lo*hi, three MMAs into the same fp32 accumulator: relative error ~2^-16 per
+//                 product, which keeps the fused features within 1e-4 of the fp32 oracle.
+//
+// Weights are pre-packed once per call (k_pack_weights) into the shared-memory operand image, chunked along K;
+// when a whole layer fits they stay resident in shared memory for the life of the CTA, otherwise (C >= 192 in
+// fp32 mode, C = 256) chunks of 64 input channels are streamed from L2 per use.
 #include "cf_common.cuh"
+#include "cf_tcgen05.cuh"
 
 namespace cf {
+
+namespace {
+
+constexpr int kTile = 128;  // cells per tile == UMMA M
+constexpr int kThreads = 128;
+
+struct TcParams {
+    const float *bev;
+    const float *T;
+    const int32_t *knn;
+    float *out;
+    const uint8_t *wimg2;  // packed W2 image (chunked)
+    const uint8_t *wimg3;
+    const float *W1;       // for the offset columns
+    const float *b2;
+    const float *b3;
+    int32_t B, N, H, W, K, Ci;
+    float x0, y0, dx, dy;
+    int64_t tiles_per_frame, tiles_total;
+};
+
+__host__ __device__ constexpr int kc_for(int C, int NS)
+{
+    // resident when both layers' packed weights + the A tile fit in shared memory, else stream 64-wide chunks
+    return (NS == 1 ? (C <= 192) : (C <= 128)) ? C : 64;
+}
+
+__host__ __device__ constexpr int tmem_cols_for(int C)
+{
+    return 2 * C <= 32 ? 32 : 2 * C <= 64 ? 64 : 2 * C <= 128 ? 128 : 2 * C <= 256 ? 256 : 512;
+}
+
+template <int C, int NS>
+struct TcLayout {
+    static constexpr int KC = kc_for(C, NS);
+    static constexpr bool kResident = KC == C;
+    static constexpr int kChunks = C / KC;
+    static_assert(C % KC == 0 && KC % 32 == 0, "channel count must be a multiple of the K-chunk");
+    static constexpr int kWChunkBytes = NS * C * KC * 2;            // one K-chunk of one layer, all splits
+    static constexpr int kWBytes = kResident ? 2 * kWChunkBytes : kWChunkBytes;
+    static constexpr int kABytes = NS * kTile * KC * 2;
+    static constexpr int kOffA = kWBytes;
+    static constexpr int kOffF = kOffA + kABytes;                   // floats: b2, b3, w1x, w1y
+    static constexpr int kOffIdx = kOffF + 4 * C * 4;               // int32 [128][CF_MAX_K]
+    static constexpr int kOffBar = kOffIdx + kTile * CF_MAX_K * 4;  // mbarrier (8 B) + tmem ptr (4 B)
+    static constexpr int kSmemBytes = kOffBar + 16;
+    static constexpr int kTmemCols = tmem_cols_for(C);
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 (C_out, C_in) row-major weights -> packed operand image: [chunk][split][n/8][k/8 in chunk][n%8][k%8] bf16
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ W, int32_t C, int32_t KC, int32_t NS,
+                                                      uint8_t *__restrict__ img)
+{
+    const int32_t units = C * (C / 8);  // one 16-byte unit = 8 consecutive k of one n
+    const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= units) return;
+    const int32_t n = u / (C / 8), k8 = u - n * (C / 8);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = W[(size_t)n * C + k8 * 8 + i];
+    uint4 hi, lo;
+    tc::split_bf16x8(v, hi, lo, NS == 2);
+    const int32_t kc_units = KC / 8;
+    const int32_t chunk = k8 / kc_units, ku = k8 - chunk * kc_units;
+    const size_t chunk_bytes = (size_t)C * KC * 2;
+    const size_t base = (size_t)chunk * NS * chunk_bytes + tc::unit_offset(n, ku, kc_units);
+    *reinterpret_cast<uint4 *>(img + base) = hi;
+    if (NS == 2) *reinterpret_cast<uint4 *>(img + base + chunk_bytes) = lo;
+}
+
+// linear copy of a packed weight chunk (global/L2 -> shared), 16 bytes per thread per step
+__device__ __forceinline__ void copy_chunk(uint8_t *dst, const uint8_t *__restrict__ src, int bytes)
+{
+    for (int o = threadIdx.x * 16; o < bytes; o += kThreads * 16)
+        *reinterpret_cast<uint4 *>(dst + o) = __ldg(reinterpret_cast<const uint4 *>(src + o));
+}
+
+// issue the MMAs of one K-chunk: acc (+)= A[128 x KC] * Wchunk[C x KC]^T, all split products
+template <int C, int NS, int KC>
+__device__ __forceinline__ void issue_chunk(uint32_t a_addr, uint32_t w_addr, uint32_t tmem_acc, bool accumulate)
+{
+    constexpr uint32_t idesc = tc::make_idesc_bf16(kTile, C);
+    constexpr uint32_t sbo = (KC / 8) * 128, lbo = 128;
+    constexpr uint32_t a_split = kTile * KC * 2, w_split = C * KC * 2;
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll
+    for (int kk = 0; kk < KC / 16; ++kk) {
+        const uint32_t koff = kk * 2 * lbo;  // 16 bf16 = two 16-byte k-units
+        const uint64_t a_hi = tc::make_desc(a_addr + koff, lbo, sbo);
+        const uint64_t w_hi = tc::make_desc(w_addr + koff, lbo, sbo);
+        tc::mma_bf16(tmem_acc, a_hi, w_hi, idesc, acc);
+        acc = 1u;
+        if (NS == 2) {
+            const uint64_t a_lo = tc::make_desc(a_addr + a_split + koff, lbo, sbo);
+            const uint64_t w_lo = tc::make_desc(w_addr + w_split + koff, lbo, sbo);
+            tc::mma_bf16(tmem_acc, a_hi, w_lo, idesc, 1u);
+            tc::mma_bf16(tmem_acc, a_lo, w_hi, idesc, 1u);
+        }
+    }
+}
+
+template <int C, int NS>
+__global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
+{
+    using L = TcLayout<C, NS>;
+    constexpr int KC = L::KC;
+    constexpr int kc_units = KC / 8;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sW = smem;
+    uint8_t *sA = smem + L::kOffA;
+    float *sb2 = reinterpret_cast<float *>(smem + L::kOffF);
+    float *sb3 = sb2 + C;
+    float *sw1x = sb3 + C;
+    float *sw1y = sw1x + C;
+    int32_t *sidx = reinterpret_cast<int32_t *>(smem + L::kOffIdx);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int K = p.K;
+    const int64_t cells = (int64_t)p.H * p.W;
+
+    // ---- one-time setup -----------------------------------------------------------------------------------------
+    if (tid == 0) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(tmem_slot, L::kTmemCols);
+    for (int c = tid; c < C; c += kThreads) {
+        sb2[c] = __ldg(p.b2 + c);
+        sb3[c] = __ldg(p.b3 + c);
+        sw1x[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci);
+        sw1y[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci + 1);
+    }
+    if (L::kResident) {
+        copy_chunk(sW, p.wimg2, L::kWChunkBytes);
+        copy_chunk(sW + L::kWChunkBytes, p.wimg3, L::kWChunkBytes);
+        tc::fence_proxy_async();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc = tmem_base;                                // columns [0, C)
+    const uint32_t tmem_pool = tmem_base + C;                           // columns [C, 2C)
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;              // this warp's TMEM lanes
+    const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
+    uint32_t phase = 0;
+
+    for (int64_t tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const int b = (int)(tile / p.tiles_per_frame);
+        const int64_t cell0 = (tile - (int64_t)b * p.tiles_per_frame) * kTile;
+        const int64_t cell = cell0 + tid;  // this thread's row
+        const bool in_range = cell < cells;
+
+        // ---- neighbour indices of the tile: coalesced load, then each thread reads its own row --------------------
+        {
+            const int64_t n_idx = min((int64_t)kTile, cells - cell0) * K;
+            const int32_t *src = p.knn + ((size_t)b * cells + cell0) * K;
+            for (int64_t i = tid; i < (int64_t)kTile * K; i += kThreads) sidx[i] = i < n_idx ? __ldg(src + i) : -1;
+        }
+        __syncthreads();
+        float cx = 0.f, cy = 0.f;
+        if (in_range) {
+            const int32_t i = (int32_t)(cell / p.W), j = (int32_t)(cell - (int64_t)i * p.W);
+            cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
+            cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
+        }
+        const float *Tb = p.T + (size_t)b * p.N * C;
+        int n_valid = 0;
+        bool pooled_live = false;  // uniform across the CTA
+
+        for (int k = 0; k < K; ++k) {
+            const int32_t pj = sidx[tid * K + k];
+            const bool valid = pj >= 0;
+            if (!__syncthreads_or(valid)) continue;  // nobody in the tile has a k-th neighbour
+            n_valid += valid;
+            const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(valid ? pj : 0) * C);
+
+            for (int ch = 0; ch < L::kChunks; ++ch) {
+                if (!L::kResident) copy_chunk(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                // A chunk: row `tid`, channels [ch*KC, ch*KC + KC)
+#pragma unroll 2
+                for (int ku = 0; ku < kc_units; ++ku) {
+                    const int c0 = ch * KC + ku * 8;
+                    float v[8];
+                    if (valid) {
+                        const float4 t0 = __ldg(trow + (c0 >> 2)), t1 = __ldg(trow + (c0 >> 2) + 1);
+                        const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            v[i] = fmaxf(t[i] - fmaf(sw1x[c0 + i], cx, sw1y[c0 + i] * cy), 0.0f);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+                    }
+                    uint4 hi, lo;
+                    tc::split_bf16x8(v, hi, lo, NS == 2);
+                    const uint32_t off = tc::unit_offset(tid, ku, kc_units);
+                    *reinterpret_cast<uint4 *>(sA + off) = hi;
+                    if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
+                }
+                tc::fence_proxy_async();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    tc::fence_after_sync();
+                    issue_chunk<C, NS, KC>(sA_addr, sW_addr, tmem_acc, ch > 0);
+                    tc::commit(bar);
+                }
+                tc::mbar_wait(bar, phase);
+                phase ^= 1u;
+                tc::fence_after_sync();
+            }
+            // ---- epilogue of slot k: pooled (+)= valid ? relu(acc + b2) : 0 -----------------------------------------
+            __syncwarp();
+#pragma unroll 1
+            for (int cc = 0; cc < C / 32; ++cc) {
+                float z[32], s[32];
+                tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
+                if (pooled_live) tc::tmem_ld32(tmem_pool + lane_off + cc * 32, s);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float h = valid ? fmaxf(z[i] + sb2[cc * 32 + i], 0.0f) : 0.0f;
+                    s[i] = pooled_live ? s[i] + h : h;
+                }
+                tc::tmem_st32(tmem_pool + lane_off + cc * 32, s);
+            }
+            pooled_live = true;
+            tc::fence_before_sync();  // TMEM reads/writes above are ordered before the next MMA via the next barrier
+        }
+
+        if (pooled_live) {
+            // ---- layer 3: acc = pooled * W3^T --------------------------------------------------------------------------
+            for (int ch = 0; ch < L::kChunks; ++ch) {
+                if (!L::kResident) copy_chunk(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+#pragma unroll 1
+                for (int cc = 0; cc < KC / 32; ++cc) {
+                    float s[32];
+                    tc::tmem_ld32(tmem_pool + lane_off + ch * KC + cc * 32, s);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = s[q * 8 + i];
+                        uint4 hi, lo;
+                        tc::split_bf16x8(v, hi, lo, NS == 2);
+                        const uint32_t off = tc::unit_offset(tid, cc * 4 + q, kc_units);
+                        *reinterpret_cast<uint4 *>(sA + off) = hi;
+                        if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    tc::fence_after_sync();
+                    issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : 0), tmem_acc, ch > 0);
+                    tc::commit(bar);
+                }
+                tc::mbar_wait(bar, phase);
+                phase ^= 1u;
+                tc::fence_after_sync();
+            }
+        }
+        // ---- final epilogue: out = bev + acc + n_valid * b3 (thread = cell: a warp touches 128 contiguous bytes) --
+        const float nv = (float)n_valid;
+        __syncwarp();
+#pragma unroll 1
+        for (int cc = 0; cc < C / 32; ++cc) {
+            float z[32];
+            if (pooled_live) tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
+            if (in_range) {
+                const size_t base = ((size_t)b * C + cc * 32) * cells + cell;
+                float bv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) bv[i] = __ldg(p.bev + base + (size_t)i * cells);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float add = pooled_live ? z[i] + nv * sb3[cc * 32 + i] : 0.0f;
+                    p.out[base + (size_t)i * cells] = bv[i] + add;
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();  // sidx / A / TMEM are reused by the next tile
+        tc::fence_after_sync();
+    }
+
+    __syncthreads();
+    if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);
+}
+
+// a standalone D[128 x N] = A[128 x Kd] * B[N x Kd]^T through exactly the same packing / descriptor / TMEM code,
+// so operand-layout mistakes can be told apart from fusion-logic mistakes (cf_debug_umma_gemm).
+template <int N, int NS>
+__global__ void __launch_bounds__(kThreads) k_umma_selftest(const float *__restrict__ A, const float *__restrict__ Bm,
+                                                            int32_t Kd, float *__restrict__ D)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int kc_units = Kd / 8;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + NS * kTile * Kd * 2;
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256);
+    for (int ku = 0; ku < kc_units; ++ku) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = A[(size_t)tid * Kd + ku * 8 + i];
+        uint4 hi, lo;
+        tc::split_bf16x8(v, hi, lo, NS == 2);
+        *reinterpret_cast<uint4 *>(sA + tc::unit_offset(tid, ku, kc_units)) = hi;
+        if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Kd * 2 + tc::unit_offset(tid, ku, kc_units)) = lo;
+    }
+    for (int u = tid; u < N * kc_units; u += kThreads) {
+        const int n = u / kc_units, ku = u - n * kc_units;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = Bm[(size_t)n * Kd + ku * 8 + i];
+        uint4 hi, lo;
+        tc::split_bf16x8(v, hi, lo, NS == 2);
+        *reinterpret_cast<uint4 *>(sB + tc::unit_offset(n, ku, kc_units)) = hi;
+        if (NS == 2) *reinterpret_cast<uint4 *>(sB + N * Kd * 2 + tc::unit_offset(n, ku, kc_units)) = lo;
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(kTile, N);
+        const uint32_t sbo = kc_units * 128, lbo = 128;
+        const uint32_t a0 = tc::smem_u32(sA), b0 = tc::smem_u32(sB);
+        uint32_t acc = 0;
+        for (int kk = 0; kk < Kd / 16; ++kk) {
+            const uint32_t koff = kk * 2 * lbo;
+            const uint64_t a_hi = tc::make_desc(a0 + koff, lbo, sbo), b_hi = tc::make_desc(b0 + koff, lbo, sbo);
+            tc::mma_bf16(tmem_base, a_hi, b_hi, idesc, acc);
+            acc = 1;
+            if (NS == 2) {
+                const uint64_t a_lo = tc::make_desc(a0 + kTile * Kd * 2 + koff, lbo, sbo);
+                const uint64_t b_lo = tc::make_desc(b0 + N * Kd * 2 + koff, lbo, sbo);
+                tc::mma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+                tc::mma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+            }
+        }
+        tc::commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int cc = 0; cc < N / 32; ++cc) {
+        float z[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, z);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) D[(size_t)tid * N + cc * 32 + i] = z[i];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_free(tmem_base, N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256);
+}
+
+template <int C, int NS>
+int launch_tc(const TcParams &p, cudaStream_t st)
+{
+    using L = TcLayout<C, NS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                L::kSmemBytes),
+                           "k_fusion_tc smem attribute"));
+        attr_set = true;
+    }
+    // CTAs per SM: limited by shared memory and by TMEM columns (512 per SM); never oversubscribe TMEM
+    int by_smem = (227 * 1024) / (L::kSmemBytes + 1024);
+    int by_tmem = 512 / L::kTmemCols;
+    int per_sm = std::max(1, std::min(std::min(by_smem, by_tmem), 8));
+    const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
+    k_fusion_tc<C, NS><<<(unsigned)grid, kThreads, L::kSmemBytes, st>>>(p);
+    return CF_OK;
+}
+
+}  // namespace
+
 size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode)
 {
-    (void)mode;
-    return (size_t)2 * C * C * sizeof(float);
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    return (size_t)2 * NS * C * C * 2 + 256;
 }
-int fusion_tc(const float *, const float *, const int32_t *, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t,
-              float, float, float, float, const float *, int32_t, const float *, const float *, const float *,
-              const float *, float *, int32_t, void *, cudaStream_t)
+
+int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H,
+              int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1, int32_t Ci,
+              const float *d_W2, const float *d_b2, const float *d_W3, const float *d_b3, float *d_out, int32_t mode,
+              void *d_workspace, cudaStream_t st)
 {
-    set_error("cf_fusion_fwd: tcgen05 path not built yet; use CF_MODE_FP32_SIMT");
-    return CF_ERR_UNSUPPORTED;
+    CF_REQUIRE(C % 32 == 0, CF_ERR_UNSUPPORTED, "cf_fusion_fwd: tensor-core path needs C %% 32 == 0 (C=%d)", C);
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    const int KC = kc_for(C, NS);
+    uint8_t *img2 = (uint8_t *)d_workspace;
+    uint8_t *img3 = img2 + (size_t)NS * C * C * 2;
+    const int pack_blocks = (C * (C / 8) + 255) / 256;
+    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, KC, NS, img2);
+    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, KC, NS, img3);
+    TcParams p;
+    p.bev = d_bev; p.T = d_T; p.knn = d_knn; p.out = d_out; p.wimg2 = img2; p.wimg3 = img3; p.W1 = d_W1;
+    p.b2 = d_b2; p.b3 = d_b3; p.B = B; p.N = N; p.H = H; p.W = W; p.K = K; p.Ci = Ci;
+    p.x0 = x0; p.y0 = y0; p.dx = dx; p.dy = dy;
+    p.tiles_per_frame = ceil_div64((int64_t)H * W, kTile);
+    p.tiles_total = p.tiles_per_frame * B;
+    int rc = CF_ERR_UNSUPPORTED;
+#define CF_TC_CASE(c)                                                          \
+    case c:                                                                    \
+        rc = NS == 2 ? launch_tc<c, 2>(p, st) : launch_tc<c, 1>(p, st);        \
+        break;
+    switch (C) {
+        CF_TC_CASE(32) CF_TC_CASE(64) CF_TC_CASE(96) CF_TC_CASE(128) CF_TC_CASE(192) CF_TC_CASE(256)
+        default:
+            set_error("cf_fusion_fwd: unsupported C=%d on the tensor-core path", C);
+            return CF_ERR_UNSUPPORTED;
+    }
+#undef CF_TC_CASE
+    CF_TRY(rc);
+    count_launches(3);
+    return launch_status("cf_fusion_fwd (tcgen05)");
 }
+
+int umma_selftest(const float *d_A, const float *d_B, int32_t N, int32_t Kd, int32_t split, float *d_D, cudaStream_t st)
+{
+    CF_REQUIRE(Kd % 16 == 0 && Kd >= 16 && Kd <= 256, CF_ERR_ARG, "cf_debug_umma_gemm: K=%d", Kd);
+    const int NS = split ? 2 : 1;
+    const size_t smem = (size_t)NS * (kTile + N) * Kd * 2;
+    CF_REQUIRE(smem <= 200 * 1024, CF_ERR_ARG, "cf_debug_umma_gemm: operands do not fit in shared memory");
+#define CF_ST_CASE(n)                                                                                                  \
+    case n:                                                                                                            \
+        if (NS == 2) {                                                                                                 \
+            CF_TRY(cuda_status(cudaFuncSetAttribute(k_umma_selftest<n, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                    200 * 1024), "selftest attr"));                                   \
+            k_umma_selftest<n, 2><<<1, kThreads, smem, st>>>(d_A, d_B, Kd, d_D);                                       \
+        } else {                                                                                                       \
+            CF_TRY(cuda_status(cudaFuncSetAttribute(k_umma_selftest<n, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                    200 * 1024), "selftest attr"));                                   \
+            k_umma_selftest<n, 1><<<1, kThreads, smem, st>>>(d_A, d_B, Kd, d_D);                                       \
+        }                                                                                                              \
+        break;
+    switch (N) {
+        CF_ST_CASE(32) CF_ST_CASE(64) CF_ST_CASE(128) CF_ST_CASE(192) CF_ST_CASE(256)
+        default:
+            set_error("cf_debug_umma_gemm: N=%d not instantiated", N);
+            return CF_ERR_ARG;
+    }
+#undef CF_ST_CASE
+    count_launches(1);
+    return launch_status("cf_debug_umma_gemm");
+}
+
 }  // namespace cf
+
+// D (128,N) fp32 = A (128,K) * B (N,K)^T through the library's tcgen05 building blocks; split != 0 uses the
+// bf16 hi/lo three-product scheme of CF_MODE_FP32.  Self-test entry point (tests/test_gpu_umma.py).
+extern "C" int cf_debug_umma_gemm(const float *d_A, const float *d_B, int32_t N, int32_t K, int32_t split,
+                                         float *d_D, void *stream)
+{
+    using namespace cf;
+    CF_TRY(require_sm100());
+    CF_REQUIRE(d_A && d_B && d_D, CF_ERR_ARG, "cf_debug_umma_gemm: null pointer");
+    return umma_selftest(d_A, d_B, N, K, split, d_D, (cudaStream_t)stream);
+}

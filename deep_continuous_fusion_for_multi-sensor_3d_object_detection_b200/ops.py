@@ -227,3 +227,16 @@ def box_iou(boxes_a, boxes_b, nudge_b=0.0):
         check(lib.cf_box_iou(ptr(boxes_a), na, ptr(boxes_b), nb, float(nudge_b), ptr(i3), ptr(i2), stream_ptr()),
               "cf_box_iou")
     return i3, i2
+
+
+def debug_umma_gemm(A, Bm, split=False):
+    """Self-test: D (128,N) = A (128,K) @ B (N,K)^T through the library's tcgen05 building blocks."""
+    lib = load()
+    A = _contig(A, "A", torch.float32, 2)
+    Bm = _contig(Bm, "B", torch.float32, 2)
+    if A.shape[0] != 128 or A.shape[1] != Bm.shape[1]:
+        raise ValueError("debug_umma_gemm: A must be (128,K) and B (N,K)")
+    D = torch.empty((128, Bm.shape[0]), dtype=torch.float32, device=A.device)
+    check(lib.cf_debug_umma_gemm(ptr(A), ptr(Bm), Bm.shape[0], A.shape[1], int(bool(split)), ptr(D), stream_ptr()),
+          "cf_debug_umma_gemm")
+    return D

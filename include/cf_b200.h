@@ -152,6 +152,14 @@ CF_API int cf_sat_matrix(const float *d_boxes, int32_t n, uint8_t *d_matrix, voi
 CF_API int cf_box_iou(const float *d_boxes_a, int32_t na, const float *d_boxes_b, int32_t nb, float nudge_b,
                double *d_iou3d, double *d_iou2d, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Self-test of the tcgen05 building blocks (operand packing, shared-memory descriptors, TMEM):
+ *   D (128,N) fp32 = A (128,K) * B (N,K)^T, bf16 operands (split != 0: bf16 hi/lo, three products).
+ *   N in {32,64,128,192,256}, K % 16 == 0.  Not part of the reference-facing surface.
+ * ------------------------------------------------------------------------------------------- */
+CF_API int cf_debug_umma_gemm(const float *d_A, const float *d_B, int32_t N, int32_t K, int32_t split, float *d_D,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,12 +207,18 @@ class GpuPipeline:
             start, srt, _ = timed("cf_bucket_points", lambda: ops.bucket_points(self.points, self.counts, self.grid))
             feat, _ = timed("cf_point_gather", lambda: ops.point_gather(self.img, self.points, self.counts, calib=self.calib,
                                                                         img_size=self.size))
+            fine, fine_stride = None, 1
             for sc, layer, bev in zip(self.wl["scales"], self.layers, self.bev):
                 g = sc["group"]
                 T = timed(f"cf_point_mlp1[g{g}]", lambda: ops.point_mlp1(feat, self.points, self.counts, layer.fc1.weight,
-                                                                         layer.fc1.bias))
-                knn = timed(f"cf_knn_query[g{g}]", lambda: ops.knn_query(start, srt, self.grid, sc["H"], sc["W"], sc["geom"],
-                                                                         self.wl["radius"], self.wl["k"]))
+                                                                         layer.fc1.bias, mode=self.mode))
+                if fine is None:
+                    knn = timed(f"cf_knn_query[g{g}]", lambda: ops.knn_query(start, srt, self.grid, sc["H"], sc["W"],
+                                                                             sc["geom"], self.wl["radius"], self.wl["k"]))
+                    fine, fine_stride = knn, sc["stride"]
+                else:   # nested scales: strided copy of the finest table (what FrameContext.knn does)
+                    knn = timed(f"cf_knn_subsample[g{g}]", lambda: ops.knn_subsample(fine, sc["stride"] // fine_stride,
+                                                                                     sc["H"], sc["W"]))
                 timed(f"cf_fusion_fwd[g{g}]", lambda: ops.fusion_fwd(bev, T, knn, sc["geom"], layer.fc1.weight,
                                                                      layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
                                                                      layer.fc3.bias, mode=self.mode))

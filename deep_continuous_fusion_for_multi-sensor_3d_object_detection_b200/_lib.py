@@ -27,10 +27,12 @@ SIGNATURES = {
     "cf_bucket_points": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cf_knn_query": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32,
                                _f32, _i32, _vp, _vp]),
+    "cf_knn_subsample": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "cf_gather_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i64]),
     "cf_point_gather": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(C.c_float),
                                   _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
-    "cf_point_mlp1": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cf_point_mlp1_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "cf_point_mlp1": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "cf_fusion_workspace_bytes": (_sz, [_i32, _i32]),
     "cf_fusion_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _i32,
                                 _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

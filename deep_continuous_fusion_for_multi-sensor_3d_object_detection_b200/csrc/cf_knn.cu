@@ -136,7 +136,39 @@ static void launch_knn(const int32_t *bs, const float4 *sp, int32_t B, int32_t N
     k_knn_query<K><<<grid, 128, 0, st>>>(bs, sp, N, g, q, out);
 }
 
+// coarse[b,i,j,:] = fine[b, i*step, j*step, :]
+__global__ void __launch_bounds__(256) k_knn_subsample(const int32_t *__restrict__ fine, int32_t Hf, int32_t Wf,
+                                                       int32_t step, int32_t *__restrict__ coarse, int32_t Hc, int32_t Wc,
+                                                       int32_t K)
+{
+    const int b = blockIdx.y;
+    const int64_t n = (int64_t)Hc * Wc * K;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t k = (int32_t)(t % K);
+        const int64_t cell = t / K;
+        const int32_t i = (int32_t)(cell / Wc), j = (int32_t)(cell - (int64_t)i * Wc);
+        coarse[(size_t)b * n + t] = __ldg(fine + (((size_t)b * Hf + (size_t)i * step) * Wf + (size_t)j * step) * K + k);
+    }
+}
+
 }  // namespace cf
+
+extern "C" int cf_knn_subsample(const int32_t *d_fine, int32_t B, int32_t Hf, int32_t Wf, int32_t step,
+                                int32_t *d_coarse, int32_t Hc, int32_t Wc, int32_t K, void *stream)
+{
+    using namespace cf;
+    CF_TRY(require_sm100());
+    CF_REQUIRE(d_fine && d_coarse, CF_ERR_ARG, "cf_knn_subsample: null pointer");
+    CF_REQUIRE(B > 0 && B <= 65535 && step >= 1 && K >= 1 && K <= CF_MAX_K && Hc > 0 && Wc > 0, CF_ERR_ARG,
+               "cf_knn_subsample: bad extents");
+    CF_REQUIRE((int64_t)(Hc - 1) * step < Hf && (int64_t)(Wc - 1) * step < Wf, CF_ERR_ARG,
+               "cf_knn_subsample: coarse grid (%d,%d) x step %d does not fit in the fine grid (%d,%d)", Hc, Wc, step, Hf, Wf);
+    const int64_t n = (int64_t)Hc * Wc * K;
+    const int blocks = (int)std::min<int64_t>(ceil_div64(n, 256), 148 * 8);
+    k_knn_subsample<<<dim3(blocks, B), 256, 0, (cudaStream_t)stream>>>(d_fine, Hf, Wf, step, d_coarse, Hc, Wc, K);
+    count_launches(1);
+    return launch_status("cf_knn_subsample");
+}
 
 extern "C" int cf_knn_query(const int32_t *d_bucket_start, const float *d_sorted, int32_t B, int32_t N, float gx0,
                             float gy0, float cell, int32_t nbx, int32_t nby, int32_t H, int32_t W, float x0,

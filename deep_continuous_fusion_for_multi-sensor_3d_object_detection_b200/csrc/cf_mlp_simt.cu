@@ -220,16 +220,37 @@ int fusion_simt(const float *d_bev, const float *d_T, const int32_t *d_knn, int3
 
 }  // namespace cf
 
+namespace cf {
+size_t point_mlp1_tc_workspace_bytes(int32_t Ci, int32_t C, int32_t mode);
+int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
+                  int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T, int32_t mode,
+                  void *d_workspace, cudaStream_t st);
+}  // namespace cf
+
+extern "C" size_t cf_point_mlp1_workspace_bytes(int32_t Ci, int32_t C, int32_t mode)
+{
+    if (mode == CF_MODE_FP32_SIMT || Ci <= 0 || C <= 0) return 0;
+    return cf::point_mlp1_tc_workspace_bytes(Ci, C, mode);
+}
+
 extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
                              int32_t N, int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T,
-                             void *stream)
+                             int32_t mode, void *d_workspace, void *stream)
 {
     using namespace cf;
     CF_TRY(require_sm100());
     CF_REQUIRE(d_feat && d_points && d_num_points && d_W1 && d_b1 && d_T, CF_ERR_ARG, "cf_point_mlp1: null pointer");
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && Ci > 0 && C > 0, CF_ERR_ARG, "cf_point_mlp1: bad extents");
     CF_REQUIRE(Ci % 4 == 0, CF_ERR_ARG, "cf_point_mlp1: Ci=%d must be a multiple of 4", Ci);
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_FP32_SIMT, CF_ERR_ARG,
+               "cf_point_mlp1: unknown mode %d", mode);
     CF_REQUIRE(aligned16(d_feat) && aligned16(d_T), CF_ERR_ALIGN, "cf_point_mlp1: feat/T must be 16-byte aligned");
+    if (mode != CF_MODE_FP32_SIMT && d_workspace != nullptr) {
+        CF_REQUIRE(aligned16(d_workspace), CF_ERR_ALIGN, "cf_point_mlp1: workspace must be 16-byte aligned");
+        const int rc = point_mlp1_tc(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, mode, d_workspace,
+                                     (cudaStream_t)stream);
+        if (rc != CF_ERR_UNSUPPORTED) return rc;  // shapes without a tensor-core instantiation use the FFMA kernel
+    }
     dim3 grid((unsigned)((N + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
     k_point_mlp1<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feat, d_points, d_num_points, N, Ci, C, d_W1, d_b1, d_T);
     count_launches(1);

@@ -75,23 +75,24 @@ struct TcLayout {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// fp32 (C_out, C_in) row-major weights -> packed operand image: [chunk][split][n/8][k/8 in chunk][n%8][k%8] bf16
+// fp32 (rows, cols) weights with row stride ld -> packed operand image:
+//   [chunk][split][n/8][k/8 in chunk][n%8][k%8] bf16, chunk = KC consecutive input channels
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ W, int32_t C, int32_t KC, int32_t NS,
-                                                      uint8_t *__restrict__ img)
+__global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ W, int32_t rows, int32_t cols, int32_t ld,
+                                                      int32_t KC, int32_t NS, uint8_t *__restrict__ img)
 {
-    const int32_t units = C * (C / 8);  // one 16-byte unit = 8 consecutive k of one n
+    const int32_t units = rows * (cols / 8);  // one 16-byte unit = 8 consecutive k of one n
     const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= units) return;
-    const int32_t n = u / (C / 8), k8 = u - n * (C / 8);
+    const int32_t n = u / (cols / 8), k8 = u - n * (cols / 8);
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = W[(size_t)n * C + k8 * 8 + i];
+    for (int i = 0; i < 8; ++i) v[i] = W[(size_t)n * ld + k8 * 8 + i];
     uint4 hi, lo;
     tc::split_bf16x8(v, hi, lo, NS == 2);
     const int32_t kc_units = KC / 8;
     const int32_t chunk = k8 / kc_units, ku = k8 - chunk * kc_units;
-    const size_t chunk_bytes = (size_t)C * KC * 2;
+    const size_t chunk_bytes = (size_t)rows * KC * 2;
     const size_t base = (size_t)chunk * NS * chunk_bytes + tc::unit_offset(n, ku, kc_units);
     *reinterpret_cast<uint4 *>(img + base) = hi;
     if (NS == 2) *reinterpret_cast<uint4 *>(img + base + chunk_bytes) = lo;
@@ -321,6 +322,156 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
     if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-4a on tensor cores:  T[b, m, :] = feat[b, m, :] W1[:, :Ci]^T + W1[:, Ci:Ci+3] p_m + b1      (m < num_points[b])
+// Tile = 128 points.  W1's image part stays resident in shared memory; the rank-3 offset term and the bias are
+// added on CUDA cores in the epilogue (Ci+3 = 131 is not an MMA-friendly K).
+// ---------------------------------------------------------------------------------------------------------------
+struct Mlp1Params {
+    const float *feat;
+    const float *points;
+    const int64_t *num_points;
+    const uint8_t *wimg;
+    const float *W1;
+    const float *b1;
+    float *T;
+    int32_t B, N, Ci;
+    int32_t tiles_per_frame;
+};
+
+template <int C, int NS>
+__global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int Ci = p.Ci, kc_units = Ci / 8;
+    const int w_bytes = NS * C * Ci * 2, a_bytes = NS * kTile * Ci * 2;
+    uint8_t *sW = smem;
+    uint8_t *sA = smem + w_bytes;
+    float *sb1 = reinterpret_cast<float *>(smem + w_bytes + a_bytes);
+    float *swx = sb1 + C, *swy = swx + C, *swz = swy + C;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int kCols = C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
+    for (int c = tid; c < C; c += kThreads) {
+        const float *w = p.W1 + (size_t)c * (Ci + 3) + Ci;
+        sb1[c] = __ldg(p.b1 + c);
+        swx[c] = __ldg(w);
+        swy[c] = __ldg(w + 1);
+        swz[c] = __ldg(w + 2);
+    }
+    copy_chunk(sW, p.wimg, w_bytes);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_acc = tmem_slot;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
+    const uint32_t idesc = tc::make_idesc_bf16(kTile, C);
+    const uint32_t sbo = kc_units * 128, lbo = 128;
+    uint32_t phase = 0;
+
+    const int64_t tiles_total = (int64_t)p.tiles_per_frame * p.B;
+    for (int64_t tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+        const int b = (int)(tile / p.tiles_per_frame);
+        const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
+        const int32_t n_pts = valid_points(p.num_points, b, p.N);
+        if (m0 >= n_pts) continue;  // uniform across the CTA
+        const int32_t m = m0 + tid;
+        const bool live = m < n_pts;
+        const float4 *frow = reinterpret_cast<const float4 *>(p.feat + ((size_t)b * p.N + (live ? m : m0)) * Ci);
+        for (int ku = 0; ku < kc_units; ++ku) {
+            float v[8];
+            if (live) {
+                const float4 t0 = __ldg(frow + 2 * ku), t1 = __ldg(frow + 2 * ku + 1);
+                v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            }
+            uint4 hi, lo;
+            tc::split_bf16x8(v, hi, lo, NS == 2);
+            const uint32_t off = tc::unit_offset(tid, ku, kc_units);
+            *reinterpret_cast<uint4 *>(sA + off) = hi;
+            if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Ci * 2 + off) = lo;
+        }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            uint32_t acc = 0;
+            for (int kk = 0; kk < Ci / 16; ++kk) {
+                const uint32_t koff = kk * 2 * lbo;
+                const uint64_t a_hi = tc::make_desc(sA_addr + koff, lbo, sbo), w_hi = tc::make_desc(sW_addr + koff, lbo, sbo);
+                tc::mma_bf16(tmem_acc, a_hi, w_hi, idesc, acc);
+                acc = 1;
+                if (NS == 2) {
+                    const uint64_t a_lo = tc::make_desc(sA_addr + kTile * Ci * 2 + koff, lbo, sbo);
+                    const uint64_t w_lo = tc::make_desc(sW_addr + C * Ci * 2 + koff, lbo, sbo);
+                    tc::mma_bf16(tmem_acc, a_hi, w_lo, idesc, 1);
+                    tc::mma_bf16(tmem_acc, a_lo, w_hi, idesc, 1);
+                }
+            }
+            tc::commit(&bar);
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (live) {
+            const float *q = p.points + ((size_t)b * p.N + m) * 3;
+            px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int cc = 0; cc < C / 32; ++cc) {
+            float z[32];
+            tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
+            if (live) {
+                float4 *dst = reinterpret_cast<float4 *>(p.T + ((size_t)b * p.N + m) * C + cc * 32);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = cc * 32 + q4 * 4 + i;
+                        o[i] = z[q4 * 4 + i] + (swx[c] * px + swy[c] * py + swz[c] * pz) + sb1[c];
+                    }
+                    dst[q4] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_free(tmem_acc, kCols);
+}
+
+template <int C, int NS>
+int launch_mlp1_tc(const Mlp1Params &p, cudaStream_t st)
+{
+    const int smem = NS * (C + kTile) * p.Ci * 2 + 4 * C * 4;
+    CF_TRY(cuda_status(cudaFuncSetAttribute(k_point_mlp1_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                       "k_point_mlp1_tc smem attribute"));
+    constexpr int kCols = C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
+    const int per_sm = std::max(1, std::min(std::min((227 * 1024) / (smem + 1024), 512 / kCols), 4));
+    const int64_t tiles = (int64_t)p.tiles_per_frame * p.B;
+    const int64_t grid = std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
+    k_point_mlp1_tc<C, NS><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    return CF_OK;
+}
+
 // a standalone D[128 x N] = A[128 x Kd] * B[N x Kd]^T through exactly the same packing / descriptor / TMEM code,
 // so operand-layout mistakes can be told apart from fusion-logic mistakes (cf_debug_umma_gemm).
 template <int N, int NS>
@@ -435,8 +586,8 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     uint8_t *img2 = (uint8_t *)d_workspace;
     uint8_t *img3 = img2 + (size_t)NS * C * C * 2;
     const int pack_blocks = (C * (C / 8) + 255) / 256;
-    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, KC, NS, img2);
-    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, KC, NS, img3);
+    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, img2);
+    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, img3);
     TcParams p;
     p.bev = d_bev; p.T = d_T; p.knn = d_knn; p.out = d_out; p.wimg2 = img2; p.wimg3 = img3; p.W1 = d_W1;
     p.b2 = d_b2; p.b3 = d_b3; p.B = B; p.N = N; p.H = H; p.W = W; p.K = K; p.Ci = Ci;
@@ -458,6 +609,41 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     CF_TRY(rc);
     count_launches(3);
     return launch_status("cf_fusion_fwd (tcgen05)");
+}
+
+
+size_t point_mlp1_tc_workspace_bytes(int32_t Ci, int32_t C, int32_t mode)
+{
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    return (size_t)NS * C * Ci * 2 + 256;
+}
+
+// returns CF_ERR_UNSUPPORTED (without setting an error) when the shape has no tensor-core instantiation
+int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
+                  int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T, int32_t mode,
+                  void *d_workspace, cudaStream_t st)
+{
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    if (Ci % 16 != 0 || Ci > 256 || C % 32 != 0) return CF_ERR_UNSUPPORTED;
+    if ((size_t)NS * (C + kTile) * Ci * 2 + 4 * C * 4 > 220 * 1024) return CF_ERR_UNSUPPORTED;
+    uint8_t *img = (uint8_t *)d_workspace;
+    k_pack_weights<<<(C * (Ci / 8) + 255) / 256, 256, 0, st>>>(d_W1, C, Ci, Ci + 3, Ci, NS, img);
+    Mlp1Params p;
+    p.feat = d_feat; p.points = d_points; p.num_points = d_num_points; p.wimg = img; p.W1 = d_W1; p.b1 = d_b1; p.T = d_T;
+    p.B = B; p.N = N; p.Ci = Ci; p.tiles_per_frame = (N + kTile - 1) / kTile;
+    int rc = CF_ERR_UNSUPPORTED;
+#define CF_M1_CASE(c)                                                              \
+    case c:                                                                        \
+        rc = NS == 2 ? launch_mlp1_tc<c, 2>(p, st) : launch_mlp1_tc<c, 1>(p, st);  \
+        break;
+    switch (C) {
+        CF_M1_CASE(32) CF_M1_CASE(64) CF_M1_CASE(96) CF_M1_CASE(128) CF_M1_CASE(192) CF_M1_CASE(256)
+        default: return CF_ERR_UNSUPPORTED;
+    }
+#undef CF_M1_CASE
+    CF_TRY(rc);
+    count_launches(2);
+    return launch_status("cf_point_mlp1 (tcgen05)");
 }
 
 int umma_selftest(const float *d_A, const float *d_B, int32_t N, int32_t Kd, int32_t split, float *d_D, cudaStream_t st)

@@ -7,6 +7,7 @@ per BEV cell, K-4 fused MLP + K-sum-pool + BEV add.   All arithmetic is in libcf
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -35,9 +36,25 @@ class FrameContext:
         return self.feat
 
     def knn(self, H, W, geom, radius, K):
-        key = (H, W, tuple(float(g) for g in geom), float(radius), int(K))
-        if key not in self._knn_cache:
-            self._knn_cache[key] = ops.knn_query(self.bucket_start, self.sorted_pts, self.grid, H, W, geom, radius, K)
+        """(B,H,W,K) int32 neighbour table of one scale, computed once per batch.
+
+        The backbone's scales are nested: with the voxel-consistent centres of geometry.scale_geometry the centre
+        of coarse cell (i,j) is bit-identical to fine cell (i*2^m, j*2^m) (same x0,y0; dx,dy scaled by 2^m, an exact
+        fp32 scaling), so a coarser table is a strided copy of an already computed finer one (cf_knn_subsample)
+        instead of a second search."""
+        geom = tuple(float(g) for g in geom)
+        key = (H, W, geom, float(radius), int(K))
+        if key in self._knn_cache:
+            return self._knn_cache[key]
+        for (Hf, Wf, gf, rf, Kf), fine in self._knn_cache.items():
+            if rf != float(radius) or Kf != int(K) or gf[0] != geom[0] or gf[1] != geom[1]:
+                continue
+            for m in (2, 4, 8, 16, 32):
+                if (float(np.float32(gf[2]) * np.float32(m)) == geom[2] and float(np.float32(gf[3]) * np.float32(m)) == geom[3]
+                        and (H - 1) * m < Hf and (W - 1) * m < Wf):
+                    self._knn_cache[key] = ops.knn_subsample(fine, m, H, W)
+                    return self._knn_cache[key]
+        self._knn_cache[key] = ops.knn_query(self.bucket_start, self.sorted_pts, self.grid, H, W, geom, radius, K)
         return self._knn_cache[key]
 
 
@@ -58,7 +75,7 @@ class _FusionFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, bev, feat, points, num_points, knn_idx, geom, mode, w1, b1, w2, b2, w3, b3):
-        T = ops.point_mlp1(feat, points, num_points, w1, b1)
+        T = ops.point_mlp1(feat, points, num_points, w1, b1, mode=mode)
         out, _ = ops.fusion_fwd(bev, T, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode)
         ctx.save_for_backward(feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3)
         ctx.geom, ctx.mode = geom, mode

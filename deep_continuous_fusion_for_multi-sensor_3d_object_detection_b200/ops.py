@@ -84,6 +84,16 @@ def knn_query(bucket_start, sorted_pts, grid: BucketGrid, H, W, geom, radius, K,
     return out
 
 
+def knn_subsample(knn_fine, step, Hc, Wc):
+    """KNN table of a `step`-times coarser scale whose cell centres coincide with every step-th fine centre."""
+    lib = load()
+    knn_fine = _contig(knn_fine, "knn_fine", torch.int32, 4)
+    B, Hf, Wf, K = knn_fine.shape
+    out = torch.empty((B, Hc, Wc, K), dtype=torch.int32, device=knn_fine.device)
+    check(lib.cf_knn_subsample(ptr(knn_fine), B, Hf, Wf, int(step), ptr(out), Hc, Wc, K, stream_ptr()), "cf_knn_subsample")
+    return out
+
+
 def point_gather(img_feat, points, num_points, calib=None, uv=None, img_size=(640.0, 480.0), out=None, workspace=None):
     """K-3.  img_feat logical (B,Ci,Hf,Wf) (any strides; channels_last avoids the re-layout pass),
     points (B,N,3), exactly one of calib ((4,3) array, host) / uv ((B,N,2) device) -> feat (B,N,Ci)."""
@@ -117,7 +127,7 @@ def point_gather(img_feat, points, num_points, calib=None, uv=None, img_size=(64
     return out, workspace
 
 
-def point_mlp1(feat, points, num_points, W1, b1, out=None):
+def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspace=None):
     """K-4a.  T (B,N,C) = feat W1[:, :Ci]^T + points W1[:, Ci:]^T + b1."""
     lib = load()
     feat = _contig(feat, "feat", torch.float32, 3)
@@ -128,10 +138,14 @@ def point_mlp1(feat, points, num_points, W1, b1, out=None):
     C_out = W1.shape[0]
     if W1.shape[1] != Ci + 3 or b1.shape[0] != C_out:
         raise ValueError(f"W1/b1: expected ({C_out},{Ci + 3})/({C_out},), got {tuple(W1.shape)}/{tuple(b1.shape)}")
+    m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+    need = lib.cf_point_mlp1_workspace_bytes(Ci, C_out, m)
+    if need and (workspace is None or workspace.numel() < need):
+        workspace = torch.empty((need,), dtype=torch.uint8, device=feat.device)
     if out is None:
         out = torch.empty((B, N, C_out), dtype=torch.float32, device=feat.device)
-    check(lib.cf_point_mlp1(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, C_out, ptr(W1), ptr(b1), ptr(out),
-                            stream_ptr()), "cf_point_mlp1")
+    check(lib.cf_point_mlp1(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, C_out, ptr(W1), ptr(b1), ptr(out), m,
+                            ptr(workspace) if need else None, stream_ptr()), "cf_point_mlp1")
     return out
 
 

@@ -79,6 +79,12 @@ CF_API int cf_knn_query(const int32_t *d_bucket_start, const float *d_sorted, in
                  float gy0, float cell, int32_t nbx, int32_t nby, int32_t H, int32_t W, float x0, float y0,
                  float dx, float dy, float radius, int32_t K, int32_t *d_knn_idx, void *stream);
 
+/* The cell centres of a 2^m-times coarser scale are bit-identical to every 2^m-th centre of a finer scale
+ * (same x0,y0; dx,dy scaled by a power of two), so its KNN table is a strided copy of the finer one:
+ *   d_coarse[b,i,j,:] = d_fine[b, i*step, j*step, :]. */
+CF_API int cf_knn_subsample(const int32_t *d_fine, int32_t B, int32_t Hf, int32_t Wf, int32_t step,
+                     int32_t *d_coarse, int32_t Hc, int32_t Wc, int32_t K, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K-3  projection + bilinear gather, once per frame (Appendix A6, A7).
  *   d_img_feat  camera feature map, logical (B,Ci,Hf,Wf) fp32 with ELEMENT strides sb,sc,sh,sw
@@ -99,10 +105,13 @@ CF_API int cf_point_gather(const float *d_img_feat, int64_t sb, int64_t sc, int6
  *   T[b,p,:] = W1[:, :Ci] f_p + W1[:, Ci:Ci+3] (px,py,pz) + b1        so that for BEV cell centre c
  *   relu(W1 [f_p, p - (cx,cy,0)] + b1) = relu(T[b,p,:] - W1[:,Ci]*cx - W1[:,Ci+1]*cy)
  *   d_W1 (C, Ci+3) fp32 row-major (nn.Linear.weight layout), d_b1 (C).  d_T (B,N,C) fp32 out.
+ *   mode CF_MODE_FP32 / CF_MODE_BF16: tcgen05 GEMM over the Ci image channels (needs the workspace);
+ *   CF_MODE_FP32_SIMT, or shapes without a tensor-core instantiation: FFMA kernel.
  * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_point_mlp1_workspace_bytes(int32_t Ci, int32_t C, int32_t mode);
 CF_API int cf_point_mlp1(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
                   int32_t N, int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T,
-                  void *stream);
+                  int32_t mode, void *d_workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K-4  per-neighbour MLP layers 1b/2/3 + K-sum-pool + BEV add for one scale (Appendix A9, A10);

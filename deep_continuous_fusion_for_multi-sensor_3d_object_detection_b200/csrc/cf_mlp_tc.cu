@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ 
 }
 
 // linear copy of a packed weight chunk (global/L2 -> shared), 16 bytes per thread per step
+template <int NT>
 __device__ __forceinline__ void copy_chunk(uint8_t *dst, const uint8_t *__restrict__ src, int bytes)
 {
-    for (int o = threadIdx.x * 16; o < bytes; o += kThreads * 16)
+    for (int o = threadIdx.x * 16; o < bytes; o += NT * 16)
         *reinterpret_cast<uint4 *>(dst + o) = __ldg(reinterpret_cast<const uint4 *>(src + o));
 }
 
@@ -129,12 +130,25 @@ __device__ __forceinline__ void issue_chunk(uint32_t a_addr, uint32_t w_addr, ui
     }
 }
 
+// Thread layout: G groups of 128 threads.  Thread (row = tid % 128, grp = tid / 128) owns BEV cell `row` of the
+// tile; the G threads of a row split the 16-byte operand units of the A tile and the EW-column chunks of the
+// epilogues between them (warp w may only touch TMEM lanes 32*(w%4)..+31, which is exactly its rows).
+template <int C>
+struct TcShape {
+    static constexpr int G = C <= 64 ? 2 : C == 96 || C == 192 ? 3 : 4;
+    static constexpr int EW = C <= 32 ? 16 : 32;
+    static constexpr int kMinBlocks = C <= 32 ? 3 : C <= 64 ? 2 : 1;
+};
+
 template <int C, int NS>
-__global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
+__global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks) k_fusion_tc(const TcParams p)
 {
     using L = TcLayout<C, NS>;
+    constexpr int G = TcShape<C>::G, EW = TcShape<C>::EW;
+    constexpr int NT = kTile * G;
     constexpr int KC = L::KC;
     constexpr int kc_units = KC / 8;
+    constexpr int kChunksE = C / EW;  // epilogue chunks over all C columns
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sW = smem;
     uint8_t *sA = smem + L::kOffA;
@@ -147,6 +161,7 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTile - 1), grp = tid / kTile;
     const int K = p.K;
     const int64_t cells = (int64_t)p.H * p.W;
 
@@ -157,15 +172,15 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(tmem_slot, L::kTmemCols);
-    for (int c = tid; c < C; c += kThreads) {
+    for (int c = tid; c < C; c += NT) {
         sb2[c] = __ldg(p.b2 + c);
         sb3[c] = __ldg(p.b3 + c);
         sw1x[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci);
         sw1y[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci + 1);
     }
     if (L::kResident) {
-        copy_chunk(sW, p.wimg2, L::kWChunkBytes);
-        copy_chunk(sW + L::kWChunkBytes, p.wimg3, L::kWChunkBytes);
+        copy_chunk<NT>(sW, p.wimg2, L::kWChunkBytes);
+        copy_chunk<NT>(sW + L::kWChunkBytes, p.wimg3, L::kWChunkBytes);
         tc::fence_proxy_async();
     }
     tc::fence_before_sync();
@@ -174,21 +189,21 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_acc = tmem_base;                                // columns [0, C)
     const uint32_t tmem_pool = tmem_base + C;                           // columns [C, 2C)
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;              // this warp's TMEM lanes
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;        // this warp's TMEM lanes == its rows
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
     uint32_t phase = 0;
 
     for (int64_t tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         const int b = (int)(tile / p.tiles_per_frame);
         const int64_t cell0 = (tile - (int64_t)b * p.tiles_per_frame) * kTile;
-        const int64_t cell = cell0 + tid;  // this thread's row
+        const int64_t cell = cell0 + row;
         const bool in_range = cell < cells;
 
         // ---- neighbour indices of the tile: coalesced load, then each thread reads its own row --------------------
         {
             const int64_t n_idx = min((int64_t)kTile, cells - cell0) * K;
             const int32_t *src = p.knn + ((size_t)b * cells + cell0) * K;
-            for (int64_t i = tid; i < (int64_t)kTile * K; i += kThreads) sidx[i] = i < n_idx ? __ldg(src + i) : -1;
+            for (int64_t i = tid; i < (int64_t)kTile * K; i += NT) sidx[i] = i < n_idx ? __ldg(src + i) : -1;
         }
         __syncthreads();
         float cx = 0.f, cy = 0.f;
@@ -202,32 +217,40 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
         bool pooled_live = false;  // uniform across the CTA
 
         for (int k = 0; k < K; ++k) {
-            const int32_t pj = sidx[tid * K + k];
+            const int32_t pj = sidx[row * K + k];
             const bool valid = pj >= 0;
             if (!__syncthreads_or(valid)) continue;  // nobody in the tile has a k-th neighbour
             n_valid += valid;
             const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(valid ? pj : 0) * C);
 
             for (int ch = 0; ch < L::kChunks; ++ch) {
-                if (!L::kResident) copy_chunk(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
-                // A chunk: row `tid`, channels [ch*KC, ch*KC + KC)
+                if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                // A chunk: row `row`, channels [ch*KC, ch*KC + KC), this thread's share of the 16-byte units
 #pragma unroll 2
-                for (int ku = 0; ku < kc_units; ++ku) {
+                for (int ku = grp; ku < kc_units; ku += G) {
                     const int c0 = ch * KC + ku * 8;
                     float v[8];
                     if (valid) {
                         const float4 t0 = __ldg(trow + (c0 >> 2)), t1 = __ldg(trow + (c0 >> 2) + 1);
-                        const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            v[i] = fmaxf(t[i] - fmaf(sw1x[c0 + i], cx, sw1y[c0 + i] * cy), 0.0f);
+                        const float4 x0 = *reinterpret_cast<const float4 *>(sw1x + c0);
+                        const float4 x1 = *reinterpret_cast<const float4 *>(sw1x + c0 + 4);
+                        const float4 y0 = *reinterpret_cast<const float4 *>(sw1y + c0);
+                        const float4 y1 = *reinterpret_cast<const float4 *>(sw1y + c0 + 4);
+                        v[0] = fmaxf(t0.x - fmaf(x0.x, cx, y0.x * cy), 0.0f);
+                        v[1] = fmaxf(t0.y - fmaf(x0.y, cx, y0.y * cy), 0.0f);
+                        v[2] = fmaxf(t0.z - fmaf(x0.z, cx, y0.z * cy), 0.0f);
+                        v[3] = fmaxf(t0.w - fmaf(x0.w, cx, y0.w * cy), 0.0f);
+                        v[4] = fmaxf(t1.x - fmaf(x1.x, cx, y1.x * cy), 0.0f);
+                        v[5] = fmaxf(t1.y - fmaf(x1.y, cx, y1.y * cy), 0.0f);
+                        v[6] = fmaxf(t1.z - fmaf(x1.z, cx, y1.z * cy), 0.0f);
+                        v[7] = fmaxf(t1.w - fmaf(x1.w, cx, y1.w * cy), 0.0f);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = 0.0f;
                     }
                     uint4 hi, lo;
                     tc::split_bf16x8(v, hi, lo, NS == 2);
-                    const uint32_t off = tc::unit_offset(tid, ku, kc_units);
+                    const uint32_t off = tc::unit_offset(row, ku, kc_units);
                     *reinterpret_cast<uint4 *>(sA + off) = hi;
                     if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
                 }
@@ -246,37 +269,43 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
             // ---- epilogue of slot k: pooled (+)= valid ? relu(acc + b2) : 0 -----------------------------------------
             __syncwarp();
 #pragma unroll 1
-            for (int cc = 0; cc < C / 32; ++cc) {
-                float z[32], s[32];
-                tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
-                if (pooled_live) tc::tmem_ld32(tmem_pool + lane_off + cc * 32, s);
+            for (int cc = grp; cc < kChunksE; cc += G) {
+                float z[EW], s[EW];
+                tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
+                if (pooled_live) tc::tmem_ld<EW>(tmem_pool + lane_off + cc * EW, s);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float h = valid ? fmaxf(z[i] + sb2[cc * 32 + i], 0.0f) : 0.0f;
-                    s[i] = pooled_live ? s[i] + h : h;
+                for (int i4 = 0; i4 < EW / 4; ++i4) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(sb2 + cc * EW + i4 * 4);
+                    const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float h = valid ? fmaxf(z[i4 * 4 + i] + bq[i], 0.0f) : 0.0f;
+                        s[i4 * 4 + i] = pooled_live ? s[i4 * 4 + i] + h : h;
+                    }
                 }
-                tc::tmem_st32(tmem_pool + lane_off + cc * 32, s);
+                tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);
             }
             pooled_live = true;
-            tc::fence_before_sync();  // TMEM reads/writes above are ordered before the next MMA via the next barrier
+            tc::fence_before_sync();  // TMEM accesses above are ordered before the next MMA by the next barrier
         }
 
         if (pooled_live) {
             // ---- layer 3: acc = pooled * W3^T --------------------------------------------------------------------------
             for (int ch = 0; ch < L::kChunks; ++ch) {
-                if (!L::kResident) copy_chunk(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                if (!L::kResident) copy_chunk<NT>(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                __syncwarp();
 #pragma unroll 1
-                for (int cc = 0; cc < KC / 32; ++cc) {
-                    float s[32];
-                    tc::tmem_ld32(tmem_pool + lane_off + ch * KC + cc * 32, s);
+                for (int cc = grp; cc < KC / EW; cc += G) {
+                    float s[EW];
+                    tc::tmem_ld<EW>(tmem_pool + lane_off + ch * KC + cc * EW, s);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < EW / 8; ++q) {
                         float v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = s[q * 8 + i];
                         uint4 hi, lo;
                         tc::split_bf16x8(v, hi, lo, NS == 2);
-                        const uint32_t off = tc::unit_offset(tid, cc * 4 + q, kc_units);
+                        const uint32_t off = tc::unit_offset(row, cc * (EW / 8) + q, kc_units);
                         *reinterpret_cast<uint4 *>(sA + off) = hi;
                         if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
                     }
@@ -298,17 +327,17 @@ __global__ void __launch_bounds__(kThreads) k_fusion_tc(const TcParams p)
         const float nv = (float)n_valid;
         __syncwarp();
 #pragma unroll 1
-        for (int cc = 0; cc < C / 32; ++cc) {
-            float z[32];
-            if (pooled_live) tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
+        for (int cc = grp; cc < kChunksE; cc += G) {
+            float z[EW];
+            if (pooled_live) tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
             if (in_range) {
-                const size_t base = ((size_t)b * C + cc * 32) * cells + cell;
-                float bv[32];
+                const size_t base = ((size_t)b * C + cc * EW) * cells + cell;
+                float bv[EW];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) bv[i] = __ldg(p.bev + base + (size_t)i * cells);
+                for (int i = 0; i < EW; ++i) bv[i] = __ldg(p.bev + base + (size_t)i * cells);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float add = pooled_live ? z[i] + nv * sb3[cc * 32 + i] : 0.0f;
+                for (int i = 0; i < EW; ++i) {
+                    const float add = pooled_live ? z[i] + nv * sb3[cc * EW + i] : 0.0f;
                     p.out[base + (size_t)i * cells] = bv[i] + add;
                 }
             }
@@ -367,7 +396,7 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
         swy[c] = __ldg(w + 1);
         swz[c] = __ldg(w + 2);
     }
-    copy_chunk(sW, p.wimg, w_bytes);
+    copy_chunk<kThreads>(sW, p.wimg, w_bytes);
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -551,6 +580,7 @@ template <int C, int NS>
 int launch_tc(const TcParams &p, cudaStream_t st)
 {
     using L = TcLayout<C, NS>;
+    constexpr int NT = kTile * TcShape<C>::G;
     static bool attr_set = false;
     if (!attr_set) {
         CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -558,12 +588,13 @@ int launch_tc(const TcParams &p, cudaStream_t st)
                            "k_fusion_tc smem attribute"));
         attr_set = true;
     }
-    // CTAs per SM: limited by shared memory and by TMEM columns (512 per SM); never oversubscribe TMEM
-    int by_smem = (227 * 1024) / (L::kSmemBytes + 1024);
-    int by_tmem = 512 / L::kTmemCols;
-    int per_sm = std::max(1, std::min(std::min(by_smem, by_tmem), 8));
+    // CTAs per SM: limited by shared memory, TMEM columns (512 per SM, never oversubscribed) and threads
+    const int by_smem = (227 * 1024) / (L::kSmemBytes + 1024);
+    const int by_tmem = 512 / L::kTmemCols;
+    const int by_threads = 2048 / NT;
+    const int per_sm = std::max(1, std::min(std::min(by_smem, by_tmem), std::min(by_threads, 8)));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
-    k_fusion_tc<C, NS><<<(unsigned)grid, kThreads, L::kSmemBytes, st>>>(p);
+    k_fusion_tc<C, NS><<<(unsigned)grid, NT, L::kSmemBytes, st>>>(p);
     return CF_OK;
 }
 

@@ -137,6 +137,42 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32])
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <int EW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[EW]);
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+template <int EW> __device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[EW]);
+template <> __device__ __forceinline__ void tmem_st<32>(uint32_t taddr, const float (&v)[32]) { tmem_st32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const float (&v)[16]) { tmem_st16(taddr, v); }
+
 // ---- operand packing -------------------------------------------------------------------------------------------
 // byte offset of the 16-byte unit (row r, k-unit ku) inside an R x KC tile (KC/8 units per row)
 __device__ __forceinline__ uint32_t unit_offset(int r, int ku, int kc_units)
@@ -146,17 +182,22 @@ __device__ __forceinline__ uint32_t unit_offset(int r, int ku, int kc_units)
 
 // split 8 fp32 into bf16 "hi" (round to nearest) and bf16 "lo" (the rounded residual): hi + lo carries ~16
 // mantissa bits, so hi*hi + hi*lo + lo*hi reproduces an fp32 product to ~2^-16 relative.
+// cvt.rn.bf16x2.f32 converts a pair per instruction; the bf16 -> fp32 widening is a shift / mask.
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b (high half)
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
 __device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4 &hi, uint4 &lo, bool want_lo)
 {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         if (want_lo) {
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-            l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const float a_hi = __uint_as_float(h[i] << 16), b_hi = __uint_as_float(h[i] & 0xFFFF0000u);
+            l[i] = pack_bf16x2(v[2 * i] - a_hi, v[2 * i + 1] - b_hi);
         } else {
             l[i] = 0;
         }

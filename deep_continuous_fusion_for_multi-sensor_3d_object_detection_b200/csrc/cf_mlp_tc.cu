@@ -69,7 +69,8 @@ struct TcLayout {
     static constexpr int kOffA = kWBytes;
     static constexpr int kOffF = kOffA + kABytes;                   // floats: b2, b3, w1x, w1y
     static constexpr int kOffIdx = kOffF + 4 * C * 4;               // int32 [128][CF_MAX_K]
-    static constexpr int kOffBar = kOffIdx + kTile * CF_MAX_K * 4;  // mbarrier (8 B) + tmem ptr (4 B)
+    static constexpr int kOffCtr = kOffIdx + kTile * CF_MAX_K * 4;  // float cx[128], cy[128]
+    static constexpr int kOffBar = kOffCtr + 2 * kTile * 4;         // mbarrier (8 B) + tmem ptr (4 B)
     static constexpr int kSmemBytes = kOffBar + 16;
     static constexpr int kTmemCols = tmem_cols_for(C);
 };
@@ -157,11 +158,14 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     float *sw1x = sb3 + C;
     float *sw1y = sw1x + C;
     int32_t *sidx = reinterpret_cast<int32_t *>(smem + L::kOffIdx);
+    float *scx = reinterpret_cast<float *>(smem + L::kOffCtr);
+    float *scy = scx + kTile;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), grp = tid / kTile;
+    constexpr int NW = NT / 32;
     const int K = p.K;
     const int64_t cells = (int64_t)p.H * p.W;
 
@@ -205,13 +209,17 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             const int32_t *src = p.knn + ((size_t)b * cells + cell0) * K;
             for (int64_t i = tid; i < (int64_t)kTile * K; i += NT) sidx[i] = i < n_idx ? __ldg(src + i) : -1;
         }
-        __syncthreads();
-        float cx = 0.f, cy = 0.f;
-        if (in_range) {
-            const int32_t i = (int32_t)(cell / p.W), j = (int32_t)(cell - (int64_t)i * p.W);
-            cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
-            cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
+        if (tid < kTile) {
+            float cx = 0.f, cy = 0.f;
+            if (in_range) {
+                const int32_t i = (int32_t)(cell / p.W), j = (int32_t)(cell - (int64_t)i * p.W);
+                cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
+                cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
+            }
+            scx[row] = cx;
+            scy[row] = cy;
         }
+        __syncthreads();
         const float *Tb = p.T + (size_t)b * p.N * C;
         int n_valid = 0;
         bool pooled_live = false;  // uniform across the CTA
@@ -221,36 +229,41 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             const bool valid = pj >= 0;
             if (!__syncthreads_or(valid)) continue;  // nobody in the tile has a k-th neighbour
             n_valid += valid;
-            const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(valid ? pj : 0) * C);
 
             for (int ch = 0; ch < L::kChunks; ++ch) {
                 if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
-                // A chunk: row `row`, channels [ch*KC, ch*KC + KC), this thread's share of the 16-byte units
+                // A chunk [128 rows x KC]: a warp takes one 8-row group x 4 operand units (32 channels) per step:
+                // lane (r8 = lane/4, u = lane%4).  Global side: the 4 lanes of a row read one contiguous 128-byte
+                // segment of the point's T row (2 wavefronts per row instead of 8 with a thread-per-row gather);
+                // shared side: the warp's 32 units form 512 contiguous bytes of the operand image (conflict free).
 #pragma unroll 2
-                for (int ku = grp; ku < kc_units; ku += G) {
+                for (int item = warp; item < 16 * (kc_units / 4); item += NW) {
+                    const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
+                    const int r = rg * 8 + (lane >> 2), ku = uq * 4 + (lane & 3);
                     const int c0 = ch * KC + ku * 8;
+                    const int32_t pr = sidx[r * K + k];
+                    const bool ok = pr >= 0;
+                    const float cx = scx[r], cy = scy[r];
+                    const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(ok ? pr : 0) * C + c0);
+                    const float4 t0 = __ldg(trow), t1 = __ldg(trow + 1);
+                    const float4 x0 = *reinterpret_cast<const float4 *>(sw1x + c0);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(sw1x + c0 + 4);
+                    const float4 y0 = *reinterpret_cast<const float4 *>(sw1y + c0);
+                    const float4 y1 = *reinterpret_cast<const float4 *>(sw1y + c0 + 4);
                     float v[8];
-                    if (valid) {
-                        const float4 t0 = __ldg(trow + (c0 >> 2)), t1 = __ldg(trow + (c0 >> 2) + 1);
-                        const float4 x0 = *reinterpret_cast<const float4 *>(sw1x + c0);
-                        const float4 x1 = *reinterpret_cast<const float4 *>(sw1x + c0 + 4);
-                        const float4 y0 = *reinterpret_cast<const float4 *>(sw1y + c0);
-                        const float4 y1 = *reinterpret_cast<const float4 *>(sw1y + c0 + 4);
-                        v[0] = fmaxf(t0.x - fmaf(x0.x, cx, y0.x * cy), 0.0f);
-                        v[1] = fmaxf(t0.y - fmaf(x0.y, cx, y0.y * cy), 0.0f);
-                        v[2] = fmaxf(t0.z - fmaf(x0.z, cx, y0.z * cy), 0.0f);
-                        v[3] = fmaxf(t0.w - fmaf(x0.w, cx, y0.w * cy), 0.0f);
-                        v[4] = fmaxf(t1.x - fmaf(x1.x, cx, y1.x * cy), 0.0f);
-                        v[5] = fmaxf(t1.y - fmaf(x1.y, cx, y1.y * cy), 0.0f);
-                        v[6] = fmaxf(t1.z - fmaf(x1.z, cx, y1.z * cy), 0.0f);
-                        v[7] = fmaxf(t1.w - fmaf(x1.w, cx, y1.w * cy), 0.0f);
-                    } else {
+                    v[0] = fmaxf(t0.x - fmaf(x0.x, cx, y0.x * cy), 0.0f);
+                    v[1] = fmaxf(t0.y - fmaf(x0.y, cx, y0.y * cy), 0.0f);
+                    v[2] = fmaxf(t0.z - fmaf(x0.z, cx, y0.z * cy), 0.0f);
+                    v[3] = fmaxf(t0.w - fmaf(x0.w, cx, y0.w * cy), 0.0f);
+                    v[4] = fmaxf(t1.x - fmaf(x1.x, cx, y1.x * cy), 0.0f);
+                    v[5] = fmaxf(t1.y - fmaf(x1.y, cx, y1.y * cy), 0.0f);
+                    v[6] = fmaxf(t1.z - fmaf(x1.z, cx, y1.z * cy), 0.0f);
+                    v[7] = fmaxf(t1.w - fmaf(x1.w, cx, y1.w * cy), 0.0f);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-                    }
+                    for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.0f;
                     uint4 hi, lo;
                     tc::split_bf16x8(v, hi, lo, NS == 2);
-                    const uint32_t off = tc::unit_offset(row, ku, kc_units);
+                    const uint32_t off = tc::unit_offset(r, ku, kc_units);
                     *reinterpret_cast<uint4 *>(sA + off) = hi;
                     if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
                 }

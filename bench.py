@@ -229,23 +229,19 @@ class GpuPipeline:
 def run_gpu(args):
     import torch
     import dcf_b200 as dcf
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = dcf.dist_util.env_rank_world()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+    import torch.distributed as dist
+    dcf.dist_util.init("nccl", device)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        dcf.dist_util.barrier()
         torch.cuda.synchronize()
 
-    wl = dcf.synthetic.make_workload(args.workload, seed=100 + rank)   # disjoint frames per rank
+    wl = dcf.synthetic.make_workload(args.workload, seed=dcf.dist_util.rank_seed(100, rank))   # disjoint frames per rank
     B = wl["points"].shape[0]
     mode = args.mode or wl["workload"]["mode"]
     pipe = GpuPipeline(dcf, wl, mode, device)
@@ -328,10 +324,7 @@ def run_gpu(args):
     ms_e2e = f0.elapsed_time(f1)
 
     # ---- max over ranks ---------------------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = dcf.dist_util.max_over_ranks([ms, ms_e2e], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -374,7 +367,7 @@ def run_gpu(args):
         cpu = {"value": round(v, 6), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc}
 
     line = {
-        "metric": METRIC, "value": round(B * world * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": round(dcf.dist_util.aggregate_rate(B, world, args.steps, ms), 2), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if mode in ("fp32", "simt") else "bf16",
         "data": "synthetic",
@@ -383,7 +376,7 @@ def run_gpu(args):
                                f"~{int(n_valid)} LiDAR points/frame, 128x120x160 camera map)",
                    "mlp_mode": mode, "frames_per_step_per_gpu": B, "l2_policy": "inputs_exceed_l2 (BEV in+out "
                    f"{2 * sum(b.numel() * 4 for b in pipe.bev) / 1e6:.0f} MB per step vs 126 MB L2)"},
-        "e2e": {"value": round(B * world * e2e_steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        "e2e": {"value": round(dcf.dist_util.aggregate_rate(B, world, e2e_steps, ms_e2e), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
         "gpu_launches": int(launches),
         "roofline": roof,

@@ -6,7 +6,7 @@ Chanuk-Yang/Deep_Continuous_Fusion_for_Multi-Sensor_3D_Object_Detection.
 Host side: Python / PyTorch (device memory, streams).  Device side: libcf_b200.so, hand-written sm_100a
 kernels behind the C ABI in include/cf_b200.h.  There is no CPU or PyTorch fallback.
 """
-from . import geometry, synthetic  # noqa: F401  (pure numpy, importable without the CUDA library)
+from . import dist_util, geometry, synthetic  # noqa: F401  (importable without the CUDA library)
 from ._lib import SO_PATH, build, load  # noqa: F401
 from .fusion import ContinuousFusion, FrameContext, prepare_frames  # noqa: F401
 from .postprocess import PostProcess  # noqa: F401

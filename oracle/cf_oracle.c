@@ -31,6 +31,14 @@
 
 CFO_API int cfo_version(void) { return 1; }
 
+#ifdef _OPENMP
+#include <omp.h>
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every host core, so set it explicitly. */
+CFO_API int cfo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+CFO_API int cfo_set_threads(int n) { (void)n; return 1; }
+#endif
+
 /* ------------------------------------------------------------------------------------------
  * K-2  bounded-radius KNN, brute force.   SURVEY.md Appendix A1-A5.
  *   candidates: rows < n_valid of pts (N,3)                                   (A1)

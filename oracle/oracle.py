@@ -36,6 +36,8 @@ def lib():
     if _lib is None:
         build()
         L = C.CDLL(_SO)
+        L.cfo_set_threads.argtypes = [C.c_int]
+        L.cfo_set_threads.restype = C.c_int
         L.cfo_knn_bruteforce.argtypes = [_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                          C.c_float, C.c_float, C.c_float, C.c_int32, _i32p, C.c_int64, C.c_int64]
         L.cfo_project_points.argtypes = [_f32p, C.c_int32, _f32p, _f32p]
@@ -64,6 +66,11 @@ def lib():
         L.cfo_get_bboxes.restype = C.c_int32
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """Use n OpenMP threads (returns the count in effect)."""
+    return int(lib().cfo_set_threads(int(n)))
 
 
 def _f32(a):

@@ -163,11 +163,11 @@ def cpu_port_time(wl, budget_s=15.0, threads=None):
 class GpuPipeline:
     """Device-resident buffers + the op sequence of one step (through the package's public ops / modules)."""
 
-    def __init__(self, dcf, wl, mode, device):
+    def __init__(self, dcf, wl, mode, device, bucket_size=None):
         import torch
         self.torch, self.dcf, self.wl, self.mode = torch, dcf, wl, mode
         self.device = device
-        self.grid = dcf.ops.BucketGrid(*dcf.geometry.bucket_grid(wl["config"]))
+        self.grid = dcf.ops.BucketGrid(*dcf.geometry.bucket_grid(wl["config"], bucket_size))
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.points, self.counts = dev(wl["points"]), dev(wl["num_points"])
         self.img = dev(wl["img_feat"])
@@ -247,7 +247,7 @@ def run_gpu(args):
     wl = dcf.synthetic.make_workload(args.workload, seed=dcf.dist_util.rank_seed(100, rank))   # disjoint frames per rank
     B = wl["points"].shape[0]
     mode = args.mode or wl["workload"]["mode"]
-    pipe = GpuPipeline(dcf, wl, mode, device)
+    pipe = GpuPipeline(dcf, wl, mode, device, args.bucket_size)
     lib = dcf.load()
 
     # ---- device-resident throughput -------------------------------------------------------------------
@@ -432,6 +432,7 @@ def main():
     ap.add_argument("--mode", default=None, help="fp32 | bf16 | simt (default: the workload's)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-size", type=float, default=None, help="K-1 bucket pitch in metres (default: config)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -33,7 +33,7 @@ SIGNATURES = {
                                   _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
     "cf_point_mlp1_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "cf_point_mlp1": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "cf_fusion_workspace_bytes": (_sz, [_i32, _i32]),
+    "cf_fusion_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cf_fusion_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _i32,
                                 _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "cf_get_bboxes": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),

@@ -8,18 +8,18 @@ int fusion_simt(const float *d_bev, const float *d_T, const int32_t *d_knn, int3
                 int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1,
                 int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3, const float *d_b3,
                 float *d_out, void *d_workspace, cudaStream_t st);
-size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode);
+size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W);
 int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C,
               int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1,
               int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3, const float *d_b3,
               float *d_out, int32_t mode, void *d_workspace, cudaStream_t st);
 }  // namespace cf
 
-extern "C" size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode)
+extern "C" size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W)
 {
-    if (C <= 0) return 0;
+    if (C <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
     if (mode == CF_MODE_FP32_SIMT) return cf::fusion_simt_workspace_bytes(C);
-    return cf::fusion_tc_workspace_bytes(C, mode);
+    return cf::fusion_tc_workspace_bytes(C, mode, B, H, W);
 }
 
 extern "C" int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_knn_idx, int32_t B, int32_t N,

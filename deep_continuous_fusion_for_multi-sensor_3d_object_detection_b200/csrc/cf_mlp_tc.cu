@@ -44,6 +44,8 @@ struct TcParams {
     int32_t B, N, H, W, K, Ci;
     float x0, y0, dx, dy;
     int64_t tiles_per_frame, tiles_total;
+    const int32_t *cell_list;   // (B, cells) compacted indices of the cells that have at least one neighbour
+    const int32_t *cell_count;  // (B)
 };
 
 __host__ __device__ constexpr int kc_for(int C, int NS)
@@ -70,7 +72,8 @@ struct TcLayout {
     static constexpr int kOffF = kOffA + kABytes;                   // floats: b2, b3, w1x, w1y
     static constexpr int kOffIdx = kOffF + 4 * C * 4;               // int32 [128][CF_MAX_K]
     static constexpr int kOffCtr = kOffIdx + kTile * CF_MAX_K * 4;  // float cx[128], cy[128]
-    static constexpr int kOffBar = kOffCtr + 2 * kTile * 4;         // mbarrier (8 B) + tmem ptr (4 B)
+    static constexpr int kOffCell = kOffCtr + 2 * kTile * 4;        // int32 cell index of each row
+    static constexpr int kOffBar = kOffCell + kTile * 4;            // mbarrier (8 B) + tmem ptr (4 B)
     static constexpr int kSmemBytes = kOffBar + 16;
     static constexpr int kTmemCols = tmem_cols_for(C);
 };
@@ -131,6 +134,45 @@ __device__ __forceinline__ void issue_chunk(uint32_t a_addr, uint32_t w_addr, ui
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Cell compaction.  Only ~1/3 of the BEV cells of a LiDAR frame have a point within the radius.  This pass
+//   * appends the index of every cell with a neighbour to a per-frame list (block-local order, one atomicAdd per
+//     block, so the list is a concatenation of ascending runs: neighbouring list entries are neighbouring cells and
+//     the fused kernel's BEV accesses stay coalesced), and
+//   * finishes the cells WITHOUT a neighbour right here: out = bev (skipped when the layer runs in place).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_compact(const int32_t *__restrict__ knn, int32_t K, int64_t cells, int32_t C,
+                                                      const float *__restrict__ bev, float *__restrict__ out,
+                                                      int32_t *__restrict__ list, int32_t *__restrict__ count)
+{
+    __shared__ int32_t warp_excl[8];
+    __shared__ int32_t base;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t cell = (int64_t)blockIdx.x * 256 + tid;
+    const bool inside = cell < cells;
+    const bool live = inside && __ldg(knn + ((size_t)b * cells + cell) * K) >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) warp_excl[warp] = __popc(bal);
+    __syncthreads();
+    if (tid == 0) {
+        int32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int32_t c = warp_excl[w];
+            warp_excl[w] = run;
+            run += c;
+        }
+        base = run ? atomicAdd(count + b, run) : 0;
+    }
+    __syncthreads();
+    if (live) list[(size_t)b * cells + base + warp_excl[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)cell;
+    if (inside && !live && out != bev) {
+        const size_t o = (size_t)b * C * cells + cell;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) out[o + (size_t)c * cells] = __ldg(bev + o + (size_t)c * cells);
+    }
+}
+
 // Thread layout: G groups of 128 threads.  Thread (row = tid % 128, grp = tid / 128) owns BEV cell `row` of the
 // tile; the G threads of a row split the 16-byte operand units of the A tile and the EW-column chunks of the
 // epilogues between them (warp w may only touch TMEM lanes 32*(w%4)..+31, which is exactly its rows).
@@ -160,6 +202,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     int32_t *sidx = reinterpret_cast<int32_t *>(smem + L::kOffIdx);
     float *scx = reinterpret_cast<float *>(smem + L::kOffCtr);
     float *scy = scx + kTile;
+    int32_t *scell = reinterpret_cast<int32_t *>(smem + L::kOffCell);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8);
 
@@ -198,26 +241,31 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     uint32_t phase = 0;
 
     for (int64_t tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        // tiles run over the COMPACTED list of cells that have a neighbour (k_cell_compact); cells without one were
+        // already copied bev -> out by that pass, so every row built below is (almost always) useful work
         const int b = (int)(tile / p.tiles_per_frame);
-        const int64_t cell0 = (tile - (int64_t)b * p.tiles_per_frame) * kTile;
-        const int64_t cell = cell0 + row;
-        const bool in_range = cell < cells;
-
-        // ---- neighbour indices of the tile: coalesced load, then each thread reads its own row --------------------
-        {
-            const int64_t n_idx = min((int64_t)kTile, cells - cell0) * K;
-            const int32_t *src = p.knn + ((size_t)b * cells + cell0) * K;
-            for (int64_t i = tid; i < (int64_t)kTile * K; i += NT) sidx[i] = i < n_idx ? __ldg(src + i) : -1;
-        }
+        const int64_t e0 = (tile - (int64_t)b * p.tiles_per_frame) * kTile;
+        const int32_t n_live = p.cell_list ? __ldg(p.cell_count + b) : (int32_t)cells;  // no list: every cell, in order
+        if (e0 >= n_live) continue;  // uniform
+        const bool in_range = e0 + row < n_live;
+        const int32_t cell = !in_range ? 0 : p.cell_list ? __ldg(p.cell_list + (size_t)b * cells + e0 + row) : (int32_t)(e0 + row);
         if (tid < kTile) {
             float cx = 0.f, cy = 0.f;
             if (in_range) {
-                const int32_t i = (int32_t)(cell / p.W), j = (int32_t)(cell - (int64_t)i * p.W);
+                const int32_t i = cell / p.W, j = cell - i * p.W;
                 cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
                 cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
             }
             scx[row] = cx;
             scy[row] = cy;
+            scell[row] = in_range ? cell : -1;
+        }
+        __syncthreads();
+        // neighbour indices of the tile's cells (K consecutive ints per cell; list entries are mostly consecutive cells)
+        for (int i = tid; i < kTile * K; i += NT) {
+            const int r = i / K, kk = i - r * K;
+            const int32_t cr = scell[r];
+            sidx[i] = cr >= 0 ? __ldg(p.knn + ((size_t)b * cells + cr) * K + kk) : -1;
         }
         __syncthreads();
         const float *Tb = p.T + (size_t)b * p.N * C;
@@ -613,10 +661,13 @@ int launch_tc(const TcParams &p, cudaStream_t st)
 
 }  // namespace
 
-size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode)
+static size_t tc_weight_bytes(int32_t C, int NS) { return ((size_t)2 * NS * C * C * 2 + 255) / 256 * 256; }
+
+size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W)
 {
     const int NS = mode == CF_MODE_FP32 ? 2 : 1;
-    return (size_t)2 * NS * C * C * 2 + 256;
+    // packed W2/W3 images | per-frame live-cell counts | per-frame live-cell lists
+    return tc_weight_bytes(C, NS) + 256 + (size_t)B * H * W * sizeof(int32_t);
 }
 
 int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H,
@@ -629,6 +680,19 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     const int KC = kc_for(C, NS);
     uint8_t *img2 = (uint8_t *)d_workspace;
     uint8_t *img3 = img2 + (size_t)NS * C * C * 2;
+    int32_t *cell_count = (int32_t *)((uint8_t *)d_workspace + tc_weight_bytes(C, NS));
+    int32_t *cell_list = cell_count + 64;
+    CF_REQUIRE(B <= 64, CF_ERR_ARG, "cf_fusion_fwd: batch %d > 64 frames per call", B);
+    const int64_t n_cells = (int64_t)H * W;
+    // Compaction pays when there are many more tiles than SMs; on the small coarse scales it would only reduce the
+    // number of CTAs that have work, so those run every tile (empty tiles just copy bev -> out).
+    const bool compact = ceil_div64(n_cells, kTile) * B >= 4 * (int64_t)sm_count();
+    if (compact) {
+        CF_TRY(cuda_status(cudaMemsetAsync(cell_count, 0, 256, st), "cf_fusion_fwd memset"));
+        k_cell_compact<<<dim3((unsigned)ceil_div64(n_cells, 256), (unsigned)B), 256, 0, st>>>(d_knn, K, n_cells, C, d_bev,
+                                                                                            d_out, cell_list, cell_count);
+        count_launches(1);
+    }
     const int pack_blocks = (C * (C / 8) + 255) / 256;
     k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, img2);
     k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, img3);
@@ -638,6 +702,8 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     p.x0 = x0; p.y0 = y0; p.dx = dx; p.dy = dy;
     p.tiles_per_frame = ceil_div64((int64_t)H * W, kTile);
     p.tiles_total = p.tiles_per_frame * B;
+    p.cell_list = compact ? cell_list : nullptr;
+    p.cell_count = cell_count;
     int rc = CF_ERR_UNSUPPORTED;
 #define CF_TC_CASE(c)                                                          \
     case c:                                                                    \

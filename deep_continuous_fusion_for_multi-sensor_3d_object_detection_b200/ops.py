@@ -167,7 +167,7 @@ def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None,
     b3 = _contig(b3, "b3", torch.float32, 1)
     Ci = W1.shape[1] - 3
     m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
-    need = max(lib.cf_fusion_workspace_bytes(Cc, m), 16)
+    need = max(lib.cf_fusion_workspace_bytes(Cc, m, B, H, W), 16)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=bev.device)
     if out is None:

@@ -118,9 +118,10 @@ CF_API int cf_point_mlp1(const float *d_feat, const float *d_points, const int64
  * the result replaces `x` after a residual group in ResnetCustomed.forward (model.py:74-78).
  *   out[b,:,i,j] = bev[b,:,i,j] + W3 * sum_k relu(W2 relu(T[b,idx_k,:] - e_ij) + b2) + n_valid*b3
  *   d_bev/d_out (B,C,H,W) fp32 NCHW contiguous (may alias); C % 16 == 0, 16 <= C <= 256.
- *   mode: CF_MODE_*.   d_workspace: cf_fusion_workspace_bytes(C, mode) bytes (packed weights).
+ *   mode: CF_MODE_*.   d_workspace: cf_fusion_workspace_bytes(C, mode, B, H, W) bytes (packed weights and the
+ *   compacted list of cells that have a neighbour).  B <= 64 frames per call.
  * ------------------------------------------------------------------------------------------- */
-CF_API size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode);
+CF_API size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W);
 CF_API int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_knn_idx, int32_t B, int32_t N,
                   int32_t C, int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
                   const float *d_W1, int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3,

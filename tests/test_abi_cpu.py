@@ -31,7 +31,7 @@ def test_abi_version_and_error_channel(dcf):
     lib = dcf.load()
     assert lib.cf_abi_version() == 1
     assert isinstance(lib.cf_last_error(), bytes)
-    assert lib.cf_fusion_workspace_bytes(128, 0) >= 2 * 2 * 128 * 128 * 2
+    assert lib.cf_fusion_workspace_bytes(128, 0, 2, 96, 64) >= 2 * 2 * 128 * 128 * 2 + 2 * 96 * 64 * 4
     assert lib.cf_nms_workspace_bytes(2, 2048) >= 2 * 2048 * 32 * 8
     assert lib.cf_bucket_workspace_bytes(4, 140, 124) == 4 * 140 * 124 * 4
     assert lib.cf_gather_workspace_bytes(1, 128, 120, 160, 1) == 0   # channels_last needs no re-layout

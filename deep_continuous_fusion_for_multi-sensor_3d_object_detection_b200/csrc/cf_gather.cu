@@ -53,7 +53,12 @@ __global__ void __launch_bounds__(256) k_point_gather(const float *__restrict__ 
     const int32_t n = valid_points(num_points, b, N);
     const int lane = threadIdx.x & 31;
     const int32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    for (int32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n; p += warps_per_grid) {
+    for (int32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < N; p += warps_per_grid) {
+        if (p >= n) {  // zero padding rows: nothing downstream may ever see uninitialised memory
+            float4 *z = reinterpret_cast<float4 *>(feat + ((size_t)b * N + p) * Ci);
+            for (int32_t c4 = lane; c4 < (Ci >> 2); c4 += 32) z[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
         float u, v;
         if (use_calib) {
             const float *q = points + ((size_t)b * N + p) * 3;

@@ -191,6 +191,15 @@ __global__ void __launch_bounds__(256) k_fusion_simt(const float *__restrict__ b
     }
 }
 
+int point_mlp1_simt(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
+                    int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T, cudaStream_t st)
+{
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+    k_point_mlp1<<<grid, 256, 0, st>>>(d_feat, d_points, d_num_points, N, Ci, C, d_W1, d_b1, d_T);
+    count_launches(1);
+    return launch_status("cf_point_mlp1");
+}
+
 size_t fusion_simt_workspace_bytes(int32_t C) { return (size_t)2 * C * C * sizeof(float); }
 
 int fusion_simt(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C,
@@ -251,8 +260,5 @@ extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const i
                                      (cudaStream_t)stream);
         if (rc != CF_ERR_UNSUPPORTED) return rc;  // shapes without a tensor-core instantiation use the FFMA kernel
     }
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-    k_point_mlp1<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feat, d_points, d_num_points, N, Ci, C, d_W1, d_b1, d_T);
-    count_launches(1);
-    return launch_status("cf_point_mlp1");
+    return point_mlp1_simt(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, (cudaStream_t)stream);
 }

@@ -31,8 +31,11 @@ class FrameContext:
         self._knn_cache = {}
 
     def gather(self, img_feat, calib=None, uv=None, img_size=(640.0, 480.0)):
-        self.feat, self._gather_ws = ops.point_gather(img_feat, self.points, self.num_points, calib=calib, uv=uv,
-                                                      img_size=img_size, workspace=self._gather_ws)
+        if torch.is_grad_enabled() and img_feat.requires_grad:
+            self.feat = _GatherFunction.apply(img_feat, self.points, self.num_points, calib, uv, tuple(img_size))
+        else:
+            self.feat, self._gather_ws = ops.point_gather(img_feat, self.points, self.num_points, calib=calib, uv=uv,
+                                                          img_size=img_size, workspace=self._gather_ws)
         return self.feat
 
     def knn(self, H, W, geom, radius, K):
@@ -70,6 +73,24 @@ def prepare_frames(points, num_points, img_feat, config=None, calib=None, uv=Non
     return ctx
 
 
+class _GatherFunction(torch.autograd.Function):
+    """K-3 with its adjoint: the camera map's gradient is the bilinear scatter-add of the per-point gradients."""
+
+    @staticmethod
+    def forward(ctx, img_feat, points, num_points, calib, uv, img_size):
+        feat, _ = ops.point_gather(img_feat, points, num_points, calib=calib, uv=uv, img_size=img_size)
+        ctx.save_for_backward(points, num_points, uv if uv is not None else points.new_empty(0))
+        ctx.calib, ctx.has_uv, ctx.img_size, ctx.img_like = calib, uv is not None, img_size, img_feat
+        return feat
+
+    @staticmethod
+    def backward(ctx, grad_feat):
+        points, num_points, uv = ctx.saved_tensors
+        gimg = ops.point_gather_bwd(grad_feat, ctx.img_like, points, num_points, calib=None if ctx.has_uv else ctx.calib,
+                                    uv=uv if ctx.has_uv else None, img_size=ctx.img_size)
+        return gimg, None, None, None, None, None
+
+
 class _FusionFunction(torch.autograd.Function):
     """Forward = cf_point_mlp1 + cf_fusion_fwd.  Saves indices, inputs and weights, never the gathered rows."""
 
@@ -83,9 +104,11 @@ class _FusionFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise NotImplementedError(
-            "cf_fusion_bwd (SURVEY 8a row K-4b) is not built in this round; run the layer under torch.no_grad() "
-            "or with frozen fusion weights")
+        feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3 = ctx.saved_tensors
+        gw1, gb1, gw2, gb2, gw3, gb3, gfeat = ops.fusion_bwd(grad_out, feat, points, num_points, knn_idx, ctx.geom, w1, b1,
+                                                             w2, b2, w3)
+        # d out / d bev is the identity
+        return grad_out, gfeat, None, None, None, None, None, gw1, gb1, gw2, gb2, gw3, gb3
 
 
 class ContinuousFusion(nn.Module):
@@ -132,7 +155,8 @@ class ContinuousFusion(nn.Module):
         knn_idx = frames.knn(H, W, geom, self.radius, self.k)
         args = (bev, frames.feat, frames.points, frames.num_points, knn_idx, geom, self.mode, self.fc1.weight,
                 self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias)
-        needs_grad = torch.is_grad_enabled() and (bev.requires_grad or any(p.requires_grad for p in self.parameters()))
+        needs_grad = torch.is_grad_enabled() and (bev.requires_grad or frames.feat.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
         if needs_grad:
             out = _FusionFunction.apply(*args)
         else:

@@ -178,6 +178,51 @@ def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None,
     return out, workspace
 
 
+def fusion_bwd(grad_out, feat, points, num_points, knn_idx, geom, W1, b1, W2, b2, W3, grad_feat=None):
+    """K-4b.  Returns (gW1, gb1, gW2, gb2, gW3, gb3, gfeat); d bev is grad_out itself."""
+    lib = load()
+    grad_out = _contig(grad_out, "grad_out", torch.float32, 4)
+    feat = _contig(feat, "feat", torch.float32, 3)
+    points = _contig(points, "points", torch.float32, 3)
+    knn_idx = _contig(knn_idx, "knn_idx", torch.int32, 4)
+    W1, W2, W3 = [_contig(w, "W", torch.float32, 2) for w in (W1, W2, W3)]
+    b1, b2 = _contig(b1, "b1", torch.float32, 1), _contig(b2, "b2", torch.float32, 1)
+    B, Cc, H, W = grad_out.shape
+    N, Ci, K = feat.shape[1], feat.shape[2], knn_idx.shape[3]
+    dev = grad_out.device
+    gW1, gb1 = torch.zeros_like(W1), torch.zeros_like(b1)
+    gW2, gb2 = torch.zeros_like(W2), torch.zeros_like(b2)
+    gW3, gb3 = torch.zeros_like(W3), torch.zeros((Cc,), dtype=torch.float32, device=dev)
+    gfeat = torch.zeros_like(feat) if grad_feat is None else grad_feat
+    ws = torch.empty((max(lib.cf_fusion_bwd_workspace_bytes(B, N, Cc, H, W, K), 16),), dtype=torch.uint8, device=dev)
+    x0, y0, dx, dy = [float(g) for g in geom]
+    check(lib.cf_fusion_bwd(ptr(grad_out), ptr(feat), ptr(points), ptr(num_points), ptr(knn_idx), B, N, Cc, H, W, K, x0, y0,
+                            dx, dy, ptr(W1), ptr(b1), Ci, ptr(W2), ptr(b2), ptr(W3), ptr(gW1), ptr(gb1), ptr(gW2),
+                            ptr(gb2), ptr(gW3), ptr(gb3), ptr(gfeat), ptr(ws), stream_ptr()), "cf_fusion_bwd")
+    return gW1, gb1, gW2, gb2, gW3, gb3, gfeat
+
+
+def point_gather_bwd(grad_feat, img_like, points, num_points, calib=None, uv=None, img_size=(640.0, 480.0)):
+    """Adjoint of point_gather: gradient w.r.t. the camera feature map (same shape / memory format as img_like)."""
+    lib = load()
+    grad_feat = _contig(grad_feat, "grad_feat", torch.float32, 3)
+    points = _contig(points, "points", torch.float32, 3)
+    gimg = torch.zeros_like(img_like)
+    B, Ci, Hf, Wf = gimg.shape
+    sb, sc, sh, sw = gimg.stride()
+    calib_arr = None
+    if calib is not None:
+        calib_np = np.ascontiguousarray(calib.detach().cpu().numpy() if isinstance(calib, torch.Tensor) else calib,
+                                        dtype=np.float32)
+        calib_arr = (C.c_float * 12)(*calib_np.reshape(-1).tolist())
+    else:
+        uv = _contig(uv, "uv", torch.float32, 3)
+    check(lib.cf_point_gather_bwd(ptr(grad_feat), ptr(gimg), sb, sc, sh, sw, B, Ci, Hf, Wf, ptr(points), ptr(uv), calib_arr,
+                                  ptr(num_points), points.shape[1], float(img_size[0]), float(img_size[1]), stream_ptr()),
+          "cf_point_gather_bwd")
+    return gimg
+
+
 # ------------------------------------------------------------------------------------------ post-process
 def get_bboxes(pred_cls, pred_box, thr=0.8, cap=4096):
     """P-1.  (B,4,H,W), (B,14,H,W) -> boxes (B,cap,7), counts (B,) i32 (clamped), counts_raw (B,) i32."""

@@ -91,7 +91,7 @@ CF_API int cf_knn_subsample(const int32_t *d_fine, int32_t B, int32_t Hf, int32_
  *               (NCHW contiguous or channels_last both accepted; Ci % 4 == 0)
  *   uv source   exactly one of: d_uv (B,N,2) = sample["projected_loc_uv"], data_import_carla.py:265-266;
  *               or h_calib, 12 HOST floats = CRT_tensor (4,3), data_import_carla.py:31-34,199-200
- *   d_feat      (B,N,Ci) fp32 out; rows >= num_points[b] are left untouched
+ *   d_feat      (B,N,Ci) fp32 out; rows >= num_points[b] are zero filled
  *   d_workspace cf_gather_workspace_bytes(...) bytes (pixel-major copy of the map when sc != 1)
  * ------------------------------------------------------------------------------------------- */
 CF_API size_t cf_gather_workspace_bytes(int32_t B, int32_t Ci, int32_t Hf, int32_t Wf, int64_t sc);
@@ -126,6 +126,27 @@ CF_API int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_
                   int32_t C, int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
                   const float *d_W1, int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3,
                   const float *d_b3, float *d_out, int32_t mode, void *d_workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-4b backward of cf_point_mlp1 + cf_fusion_fwd for one scale (training only).  d_gout = dL/d out (B,C,H,W);
+ * dL/d bev is d_gout itself.  Gradients are ACCUMULATED into d_gW1 (C,Ci+3), d_gb1 (C), d_gW2 (C,C), d_gb2,
+ * d_gW3, d_gb3 and d_gfeat (B,N,Ci) -- zero them first (d_gfeat collects every scale's contribution).
+ * The forward saves only indices, inputs and weights; H1/H2/pooled are recomputed into the workspace
+ * (cf_fusion_bwd_workspace_bytes).  fp32 on CUDA cores; reductions use atomics (reproducible to rounding).
+ * cf_point_gather_bwd is the adjoint of cf_point_gather: d_gimg (+)= bilinear scatter of d_gfeat; d_gimg has the
+ * camera map's logical shape and the given element strides.
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_fusion_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t H, int32_t W, int32_t K);
+CF_API int cf_fusion_bwd(const float *d_gout, const float *d_feat, const float *d_points,
+                  const int64_t *d_num_points, const int32_t *d_knn_idx, int32_t B, int32_t N, int32_t C,
+                  int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
+                  const float *d_W1, const float *d_b1, int32_t Ci, const float *d_W2, const float *d_b2,
+                  const float *d_W3, float *d_gW1, float *d_gb1, float *d_gW2, float *d_gb2, float *d_gW3,
+                  float *d_gb3, float *d_gfeat, void *d_workspace, void *stream);
+CF_API int cf_point_gather_bwd(const float *d_gfeat, float *d_gimg, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                        int32_t B, int32_t Ci, int32_t Hf, int32_t Wf, const float *d_points,
+                        const float *d_uv, const float *h_calib, const int64_t *d_num_points, int32_t N,
+                        float img_w, float img_h, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * P-1  Test.get_bboxes (test.py:88-108) on device: per frame, anchor 0 then anchor 1, cells in

@@ -1,0 +1,132 @@
+"""GPU: K-4b.  Gradients of the fused layer (w.r.t. the BEV map, the camera feature map and all six MLP
+parameters) against PyTorch autograd on a float64 restatement of the same layer (grid_sample gather, gathered rows,
+three Linear layers, masked sum-pool).  Tolerance 2e-3 relative L2 (2e-2 max norm) per gradient: the forward runs the fp32
+tensor-core mode, the backward fp32 CUDA cores with atomics."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_layer(bev, img, pts, n_valid, knn, geom, calib, w, size=(640.0, 480.0)):
+    """float64 reference of one scale, differentiable w.r.t. bev, img and the weights."""
+    B, C, H, W = bev.shape
+    x0, y0, dx, dy = [float(g) for g in geom]
+    cx = x0 + torch.arange(H, device=bev.device, dtype=torch.float64) * dx
+    cy = y0 + torch.arange(W, device=bev.device, dtype=torch.float64) * dy
+    w1, b1, w2, b2, w3, b3 = w
+    out = []
+    for b in range(B):
+        n = int(n_valid[b])
+        p = pts[b, :n]
+        q = torch.cat([p, torch.ones(n, 1, device=p.device, dtype=p.dtype)], 1) @ calib
+        u, v = q[:, 0] / q[:, 2], q[:, 1] / q[:, 2]
+        grid = torch.stack([2 * (u + 0.5) / size[0] - 1, 2 * (v + 0.5) / size[1] - 1], -1).view(1, 1, n, 2)
+        feat = F.grid_sample(img[b:b + 1], grid, mode="bilinear", padding_mode="zeros", align_corners=False)[0, :, 0].T
+        idx = knn[b].long()                                  # (H,W,K)
+        valid = (idx >= 0)
+        j = idx.clamp(min=0)
+        off = torch.stack([p[j, 0] - cx[:, None, None], p[j, 1] - cy[None, :, None], p[j, 2]], -1)
+        x = torch.cat([feat[j], off], -1)
+        h = F.relu(F.linear(F.relu(F.linear(x, w1, b1)), w2, b2))
+        pooled = (h * valid[..., None]).sum(2)
+        y = F.linear(pooled, w3) + valid.sum(2, keepdim=True) * b3
+        out.append(bev[b] + y.permute(2, 0, 1))
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "simt"])
+def test_backward_matches_autograd(dcf, mode):
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("tiny"), scales=(1, 2)), seed=21, c_img=32, img_hw=(24, 32))
+    cfg = wl["config"]
+    img = dev(wl["img_feat"]).requires_grad_(True)
+    pts, cnt = dev(wl["points"]), dev(wl["num_points"])
+    frames = dcf.FrameContext(pts, cnt, dcf.ops.BucketGrid(*dcf.geometry.bucket_grid(cfg)))
+    frames.gather(img, calib=wl["calib"])
+    layers, bevs, outs = [], [], []
+    for sc in wl["scales"]:
+        layer = dcf.ContinuousFusion(32, sc["C"], k=wl["k"], radius=wl["radius"], geom=sc["geom"], mode=mode).cuda()
+        with torch.no_grad():
+            for p_, w_ in zip((layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
+                               layer.fc3.bias), sc["weights"]):
+                p_.copy_(dev(w_))
+        bev = dev(sc["bev"]).requires_grad_(True)
+        out, knn = layer(bev, frames=frames, return_knn=True)
+        layers.append(layer); bevs.append(bev); outs.append((out, knn))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    seeds = [torch.randn(o.shape, device="cuda", generator=gen) for o, _ in outs]
+    loss = sum((o * s).sum() for (o, _), s in zip(outs, seeds))
+    loss.backward()
+
+    # float64 autograd reference on the same indices
+    img64 = dev(wl["img_feat"]).double().requires_grad_(True)
+    calib64 = dev(wl["calib"]).double()
+    ref_loss, ref_params, ref_bevs = 0.0, [], []
+    for sc, layer, (o, knn), s in zip(wl["scales"], layers, outs, seeds):
+        w64 = [p_.detach().double().requires_grad_(True) for p_ in (layer.fc1.weight, layer.fc1.bias, layer.fc2.weight,
+                                                                    layer.fc2.bias, layer.fc3.weight, layer.fc3.bias)]
+        b64 = dev(sc["bev"]).double().requires_grad_(True)
+        ro = torch_layer(b64, img64, pts.double(), wl["num_points"], knn, sc["geom"], calib64, w64)
+        assert (ro.float() - o.detach()).abs().max() / ro.abs().max() < 1e-4
+        ref_loss = ref_loss + (ro * s.double()).sum()
+        ref_params.append(w64); ref_bevs.append(b64)
+    ref_loss.backward()
+
+    def close(a, b, name, tol=2e-3):
+        # relative L2 error, plus a looser max-norm bound: a ReLU whose pre-activation is within fp32 rounding of zero
+        # can switch between the fp32 kernels and the fp64 reference, which perturbs a few entries, not the bulk
+        l2 = (a.double() - b).norm().item() / max(b.norm().item(), 1e-12)
+        mx = (a.double() - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+        assert l2 < tol and mx < 10 * tol, f"{name}: rel L2 err {l2:.3e}, rel max err {mx:.3e}"
+
+    close(img.grad, img64.grad, "d img_feat")
+    for g, (layer, w64, bev, b64) in enumerate(zip(layers, ref_params, bevs, ref_bevs)):
+        close(bev.grad, b64.grad, f"scale {g} d bev", 1e-6)
+        for name, p_, r_ in zip(["W1", "b1", "W2", "b2", "W3", "b3"], (layer.fc1.weight, layer.fc1.bias, layer.fc2.weight,
+                                                                        layer.fc2.bias, layer.fc3.weight, layer.fc3.bias), w64):
+            close(p_.grad, r_.grad, f"scale {g} d {name}")
+
+
+def test_training_step_through_the_dropin_model(dcf):
+    """Gradient step of ObjectDetection_DCF with fusion on: every fusion / camera parameter receives a finite gradient,
+    the fusion and camera weights get non-zero ones, and a small step along -grad lowers the loss (first-order check).
+    BatchNorm runs in eval mode, as it does in the reference (Test.__init__ calls net.eval(), train.py:76, test.py:37)."""
+    cfg = dcf.geometry.carla_config(fusion_scales=(1, 2, 3), fusion_k=3, max_num_pc=4096)
+    torch.manual_seed(0)
+    model = dcf.ObjectDetection_DCF(cfg).cuda().eval()
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=2, max_num_pc=4096, n_az=300), seed=22)
+    x_lidar = torch.rand(2, 32, 384, 256, device="cuda")
+    x_image = torch.randint(0, 255, (2, 3, 480, 640), device="cuda", dtype=torch.uint8)
+    target = torch.randn(2, 32, 96, 64, device="cuda")
+    extra = dict(pointcloud_raw=dev(wl["points"]), num_points_raw=torch.from_numpy(wl["num_points"]),
+                 projected_loc_uv=dev(wl["uv"]))
+
+    def loss_fn():
+        pred = model(x_lidar, x_image, **extra)
+        assert pred.shape == (2, 32, 96, 64)
+        return F.mse_loss(pred[:, :18].double(), target[:, :18].double())
+
+    loss0 = loss_fn()
+    loss0.backward()
+    gsq = 0.0
+    for name, p_ in model.named_parameters():
+        if name.startswith(("fusion.", "image_backbone.")):
+            assert p_.grad is not None and torch.isfinite(p_.grad).all(), name
+            gsq += float(p_.grad.double().pow(2).sum())
+    assert model.fusion["group1"].fc2.weight.grad.abs().max() > 0
+    assert model.fusion["group3"].fc1.weight.grad.abs().max() > 0
+    assert model.image_backbone.out.weight.grad.abs().max() > 0
+    # step only the fusion + camera parameters: the decrease must match  -lr * |g|^2  to first order
+    lr = 1e-5 * loss0.item() / gsq   # tiny: a random-init deep net is strongly curved (the pure-PyTorch groups too)
+    with torch.no_grad():
+        for name, p_ in model.named_parameters():
+            if name.startswith(("fusion.", "image_backbone.")):
+                p_ -= lr * p_.grad
+        loss1 = loss_fn()
+    predicted = lr * gsq
+    assert loss1.item() < loss0.item()
+    assert abs((loss0.item() - loss1.item()) - predicted) < 0.3 * predicted

@@ -54,9 +54,25 @@ __host__ __device__ constexpr int kc_for(int C, int NS)
     return (NS == 1 ? (C <= 192) : (C <= 128)) ? C : 64;
 }
 
-__host__ __device__ constexpr int tmem_cols_for(int C)
+// neighbour slots processed per barrier round (each has its own A tile and TMEM accumulator); > 1 only where the
+// A tiles and the resident weights still leave room for several CTAs per SM
+// launch shape of the two small-C instantiations (measured on B200, BASELINE configs[1]: several small CTAs per SM --
+// more independent tiles in flight -- beat fewer barrier rounds per tile; see profiles/README.md)
+#ifndef CF_SB32
+#define CF_SB32 1
+#define CF_SB64 1
+#define CF_G32 1
+#define CF_G64 2
+#define CF_EW32 16
+#define CF_EW64 16
+#define CF_MB32 6
+#define CF_MB64 3
+#endif
+__host__ __device__ constexpr int slots_per_round(int C, int NS) { return C <= 32 ? CF_SB32 : (C <= 64 ? CF_SB64 : (NS == 1 && C <= 128 ? 2 : 1)); }
+
+__host__ __device__ constexpr int tmem_cols_for(int cols)
 {
-    return 2 * C <= 32 ? 32 : 2 * C <= 64 ? 64 : 2 * C <= 128 ? 128 : 2 * C <= 256 ? 256 : 512;
+    return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
 }
 
 template <int C, int NS>
@@ -67,7 +83,9 @@ struct TcLayout {
     static_assert(C % KC == 0 && KC % 32 == 0, "channel count must be a multiple of the K-chunk");
     static constexpr int kWChunkBytes = NS * C * KC * 2;            // one K-chunk of one layer, all splits
     static constexpr int kWBytes = kResident ? 2 * kWChunkBytes : kWChunkBytes;
-    static constexpr int kABytes = NS * kTile * KC * 2;
+    static constexpr int SB = kResident ? slots_per_round(C, NS) : 1;
+    static constexpr int kASlotBytes = NS * kTile * KC * 2;         // one A tile (all splits)
+    static constexpr int kABytes = SB * kASlotBytes;
     static constexpr int kOffA = kWBytes;
     static constexpr int kOffF = kOffA + kABytes;                   // floats: b2, b3, w1x, w1y
     static constexpr int kOffIdx = kOffF + 4 * C * 4;               // int32 [128][CF_MAX_K]
@@ -75,7 +93,7 @@ struct TcLayout {
     static constexpr int kOffCell = kOffCtr + 2 * kTile * 4;        // int32 cell index of each row
     static constexpr int kOffBar = kOffCell + kTile * 4;            // mbarrier (8 B) + tmem ptr (4 B)
     static constexpr int kSmemBytes = kOffBar + 16;
-    static constexpr int kTmemCols = tmem_cols_for(C);
+    static constexpr int kTmemCols = tmem_cols_for((SB + 1) * C);   // SB accumulators + the pooled sum
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -178,9 +196,9 @@ __global__ void __launch_bounds__(256) k_cell_compact(const int32_t *__restrict_
 // epilogues between them (warp w may only touch TMEM lanes 32*(w%4)..+31, which is exactly its rows).
 template <int C>
 struct TcShape {
-    static constexpr int G = C <= 64 ? 2 : C == 96 || C == 192 ? 3 : 4;
-    static constexpr int EW = C <= 32 ? 16 : 32;
-    static constexpr int kMinBlocks = C <= 32 ? 3 : C <= 64 ? 2 : 1;
+    static constexpr int G = C <= 32 ? CF_G32 : C <= 64 ? CF_G64 : C == 96 || C == 192 ? 3 : 4;
+    static constexpr int EW = C <= 32 ? CF_EW32 : C <= 64 ? CF_EW64 : 32;
+    static constexpr int kMinBlocks = C <= 32 ? CF_MB32 : C <= 64 ? CF_MB64 : 1;
 };
 
 template <int C, int NS>
@@ -234,8 +252,9 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_acc = tmem_base;                                // columns [0, C)
-    const uint32_t tmem_pool = tmem_base + C;                           // columns [C, 2C)
+    constexpr int SB = L::SB;
+    const uint32_t tmem_acc = tmem_base;                                // SB accumulators: columns [s*C, (s+1)*C)
+    const uint32_t tmem_pool = tmem_base + SB * C;                      // pooled sum: columns [SB*C, (SB+1)*C)
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;        // this warp's TMEM lanes == its rows
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
     uint32_t phase = 0;
@@ -270,26 +289,29 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
         __syncthreads();
         const float *Tb = p.T + (size_t)b * p.N * C;
         int n_valid = 0;
+        for (int k = 0; k < K; ++k) n_valid += sidx[row * K + k] >= 0;
         bool pooled_live = false;  // uniform across the CTA
 
-        for (int k = 0; k < K; ++k) {
-            const int32_t pj = sidx[row * K + k];
-            const bool valid = pj >= 0;
-            if (!__syncthreads_or(valid)) continue;  // nobody in the tile has a k-th neighbour
-            n_valid += valid;
+        // neighbour slots in rounds of SB: build SB A tiles, ONE barrier, SB MMA groups, ONE commit / wait, one epilogue
+        for (int k0 = 0; k0 < K; k0 += SB) {
+            const int nb = min(SB, K - k0);
+            // slots are sorted (empty ones form a suffix): if nobody has a k0-th neighbour, nobody has a later one
+            if (!__syncthreads_or(sidx[row * K + k0] >= 0)) break;
 
             for (int ch = 0; ch < L::kChunks; ++ch) {
                 if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
-                // A chunk [128 rows x KC]: a warp takes one 8-row group x 4 operand units (32 channels) per step:
-                // lane (r8 = lane/4, u = lane%4).  Global side: the 4 lanes of a row read one contiguous 128-byte
-                // segment of the point's T row (2 wavefronts per row instead of 8 with a thread-per-row gather);
-                // shared side: the warp's 32 units form 512 contiguous bytes of the operand image (conflict free).
+                // A chunk [128 rows x KC] per slot: a warp takes one 8-row group x 4 operand units (32 channels) per
+                // step: lane (r8 = lane/4, u = lane%4).  Global side: the 4 lanes of a row read one contiguous
+                // 128-byte segment of the point's T row; shared side: the warp's 32 units form 512 contiguous bytes of
+                // the operand image (conflict free).
+                const int items_per_slot = 16 * (kc_units / 4);
 #pragma unroll 2
-                for (int item = warp; item < 16 * (kc_units / 4); item += NW) {
-                    const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
+                for (int item = warp; item < nb * items_per_slot; item += NW) {
+                    const int sl = item / items_per_slot, it = item - sl * items_per_slot;
+                    const int rg = it / (kc_units / 4), uq = it - rg * (kc_units / 4);
                     const int r = rg * 8 + (lane >> 2), ku = uq * 4 + (lane & 3);
                     const int c0 = ch * KC + ku * 8;
-                    const int32_t pr = sidx[r * K + k];
+                    const int32_t pr = sidx[r * K + k0 + sl];
                     const bool ok = pr >= 0;
                     const float cx = scx[r], cy = scy[r];
                     const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(ok ? pr : 0) * C + c0);
@@ -311,37 +333,44 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.0f;
                     uint4 hi, lo;
                     tc::split_bf16x8(v, hi, lo, NS == 2);
-                    const uint32_t off = tc::unit_offset(r, ku, kc_units);
-                    *reinterpret_cast<uint4 *>(sA + off) = hi;
-                    if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
+                    uint8_t *dst = sA + sl * L::kASlotBytes + tc::unit_offset(r, ku, kc_units);
+                    *reinterpret_cast<uint4 *>(dst) = hi;
+                    if (NS == 2) *reinterpret_cast<uint4 *>(dst + kTile * KC * 2) = lo;
                 }
                 tc::fence_proxy_async();
                 tc::fence_before_sync();
                 __syncthreads();
                 if (tid == 0) {
                     tc::fence_after_sync();
-                    issue_chunk<C, NS, KC>(sA_addr, sW_addr, tmem_acc, ch > 0);
+                    for (int sl = 0; sl < nb; ++sl)
+                        issue_chunk<C, NS, KC>(sA_addr + sl * L::kASlotBytes, sW_addr, tmem_acc + sl * C, ch > 0);
                     tc::commit(bar);
                 }
                 tc::mbar_wait(bar, phase);
                 phase ^= 1u;
                 tc::fence_after_sync();
             }
-            // ---- epilogue of slot k: pooled (+)= valid ? relu(acc + b2) : 0 -----------------------------------------
+            // ---- epilogue of the round: pooled (+)= sum over its slots of valid ? relu(acc + b2) : 0 ------------------
             __syncwarp();
 #pragma unroll 1
             for (int cc = grp; cc < kChunksE; cc += G) {
-                float z[EW], s[EW];
-                tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
-                if (pooled_live) tc::tmem_ld<EW>(tmem_pool + lane_off + cc * EW, s);
+                float s[EW];
+                if (pooled_live) {
+                    tc::tmem_ld<EW>(tmem_pool + lane_off + cc * EW, s);
+                } else {
 #pragma unroll
-                for (int i4 = 0; i4 < EW / 4; ++i4) {
-                    const float4 bb = *reinterpret_cast<const float4 *>(sb2 + cc * EW + i4 * 4);
-                    const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
+                    for (int i = 0; i < EW; ++i) s[i] = 0.0f;
+                }
+                for (int sl = 0; sl < nb; ++sl) {
+                    const bool valid = sidx[row * K + k0 + sl] >= 0;
+                    float z[EW];
+                    tc::tmem_ld<EW>(tmem_acc + sl * C + lane_off + cc * EW, z);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float h = valid ? fmaxf(z[i4 * 4 + i] + bq[i], 0.0f) : 0.0f;
-                        s[i4 * 4 + i] = pooled_live ? s[i4 * 4 + i] + h : h;
+                    for (int i4 = 0; i4 < EW / 4; ++i4) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(sb2 + cc * EW + i4 * 4);
+                        const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s[i4 * 4 + i] += valid ? fmaxf(z[i4 * 4 + i] + bq[i], 0.0f) : 0.0f;
                     }
                 }
                 tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);
@@ -651,7 +680,7 @@ int launch_tc(const TcParams &p, cudaStream_t st)
     }
     // CTAs per SM: limited by shared memory, TMEM columns (512 per SM, never oversubscribed) and threads
     const int by_smem = (227 * 1024) / (L::kSmemBytes + 1024);
-    const int by_tmem = 512 / L::kTmemCols;
+    const int by_tmem = 512 / L::kTmemCols;  // (SB + 1) * C columns per CTA, rounded up to a power of two
     const int by_threads = 2048 / NT;
     const int per_sm = std::max(1, std::min(std::min(by_smem, by_tmem), std::min(by_threads, 8)));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);

@@ -214,7 +214,8 @@ class GpuPipeline:
             for sc, layer, bev in zip(self.wl["scales"], self.layers, self.bev):
                 g = sc["group"]
                 T = timed(f"cf_point_mlp1[g{g}]", lambda: ops.point_mlp1(feat, self.points, self.counts, layer.fc1.weight,
-                                                                         layer.fc1.bias, mode=self.mode))
+                                                                         layer.fc1.bias, mode=self.mode,
+                                                                         packed=layer._packed.w1(layer.fc1.weight, self.mode)))
                 if fine is None:
                     knn = timed(f"cf_knn_query[g{g}]", lambda: ops.knn_query(start, srt, self.grid, sc["H"], sc["W"],
                                                                              sc["geom"], self.wl["radius"], self.wl["k"]))
@@ -224,7 +225,8 @@ class GpuPipeline:
                                                                                      sc["H"], sc["W"]))
                 timed(f"cf_fusion_fwd[g{g}]", lambda: ops.fusion_fwd(bev, T, knn, sc["geom"], layer.fc1.weight,
                                                                      layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
-                                                                     layer.fc3.bias, mode=self.mode))
+                                                                     layer.fc3.bias, mode=self.mode,
+                                                                     packed=layer._packed.w23(layer.fc2.weight, layer.fc3.weight, self.mode)))
         torch.cuda.synchronize()
         return [(n, a.elapsed_time(b)) for n, a, b in ev]
 

@@ -32,10 +32,13 @@ SIGNATURES = {
     "cf_point_gather": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(C.c_float),
                                   _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
     "cf_point_mlp1_workspace_bytes": (_sz, [_i32, _i32, _i32]),
-    "cf_point_mlp1": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "cf_point_mlp1": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "cf_point_mlp1_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "cf_fusion_packed_bytes": (_sz, [_i32, _i32]),
+    "cf_fusion_pack_weights": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "cf_fusion_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cf_fusion_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _i32,
-                                _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+                                _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "cf_fusion_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "cf_fusion_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32,
                                 _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

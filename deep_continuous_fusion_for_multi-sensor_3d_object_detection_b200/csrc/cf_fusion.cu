@@ -12,8 +12,27 @@ size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, 
 int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C,
               int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1,
               int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3, const float *d_b3,
-              float *d_out, int32_t mode, void *d_workspace, cudaStream_t st);
+              float *d_out, int32_t mode, const void *d_packed, void *d_workspace, cudaStream_t st);
+size_t fusion_tc_packed_bytes(int32_t C, int32_t mode);
+int fusion_tc_pack(const float *d_W2, const float *d_W3, int32_t C, int32_t mode, void *d_packed, cudaStream_t st);
 }  // namespace cf
+
+extern "C" size_t cf_fusion_packed_bytes(int32_t C, int32_t mode)
+{
+    if (C <= 0 || mode == CF_MODE_FP32_SIMT) return 0;
+    return cf::fusion_tc_packed_bytes(C, mode);
+}
+
+extern "C" int cf_fusion_pack_weights(const float *d_W2, const float *d_W3, int32_t C, int32_t mode, void *d_packed,
+                                      void *stream)
+{
+    using namespace cf;
+    CF_TRY(require_sm100());
+    CF_REQUIRE(d_W2 && d_W3 && d_packed, CF_ERR_ARG, "cf_fusion_pack_weights: null pointer");
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_fusion_pack_weights: mode %d has no packed form", mode);
+    CF_REQUIRE(aligned16(d_packed), CF_ERR_ALIGN, "cf_fusion_pack_weights: buffer must be 16-byte aligned");
+    return fusion_tc_pack(d_W2, d_W3, C, mode, d_packed, (cudaStream_t)stream);
+}
 
 extern "C" size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W)
 {
@@ -25,8 +44,8 @@ extern "C" size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode, int32_t B, 
 extern "C" int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_knn_idx, int32_t B, int32_t N,
                              int32_t C, int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
                              const float *d_W1, int32_t Ci, const float *d_W2, const float *d_b2,
-                             const float *d_W3, const float *d_b3, float *d_out, int32_t mode, void *d_workspace,
-                             void *stream)
+                             const float *d_W3, const float *d_b3, float *d_out, int32_t mode, const void *d_packed,
+                             void *d_workspace, void *stream)
 {
     using namespace cf;
     CF_TRY(require_sm100());
@@ -43,8 +62,9 @@ extern "C" int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t
                                d_b3, d_out, d_workspace, st);
         case CF_MODE_FP32:
         case CF_MODE_BF16:
+            CF_REQUIRE(d_packed == nullptr || aligned16(d_packed), CF_ERR_ALIGN, "cf_fusion_fwd: packed weights must be 16-byte aligned");
             return fusion_tc(d_bev, d_T, d_knn_idx, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_W2, d_b2, d_W3,
-                             d_b3, d_out, mode, d_workspace, st);
+                             d_b3, d_out, mode, d_packed, d_workspace, st);
         default:
             set_error("cf_fusion_fwd: unknown mode %d", mode);
             return CF_ERR_ARG;

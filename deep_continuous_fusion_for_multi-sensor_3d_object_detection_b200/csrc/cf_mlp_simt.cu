@@ -233,8 +233,18 @@ namespace cf {
 size_t point_mlp1_tc_workspace_bytes(int32_t Ci, int32_t C, int32_t mode);
 int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
                   int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T, int32_t mode,
-                  void *d_workspace, cudaStream_t st);
+                  const void *d_packed, void *d_workspace, cudaStream_t st);
+int point_mlp1_tc_pack(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, cudaStream_t st);
 }  // namespace cf
+
+extern "C" int cf_point_mlp1_pack_weights(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, void *stream)
+{
+    using namespace cf;
+    CF_TRY(require_sm100());
+    CF_REQUIRE(d_W1 && d_packed && aligned16(d_packed), CF_ERR_ARG, "cf_point_mlp1_pack_weights: bad pointer");
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_point_mlp1_pack_weights: mode %d has no packed form", mode);
+    return point_mlp1_tc_pack(d_W1, Ci, C, mode, d_packed, (cudaStream_t)stream);
+}
 
 extern "C" size_t cf_point_mlp1_workspace_bytes(int32_t Ci, int32_t C, int32_t mode)
 {
@@ -244,7 +254,7 @@ extern "C" size_t cf_point_mlp1_workspace_bytes(int32_t Ci, int32_t C, int32_t m
 
 extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
                              int32_t N, int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T,
-                             int32_t mode, void *d_workspace, void *stream)
+                             int32_t mode, const void *d_packed, void *d_workspace, void *stream)
 {
     using namespace cf;
     CF_TRY(require_sm100());
@@ -254,10 +264,10 @@ extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const i
     CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_FP32_SIMT, CF_ERR_ARG,
                "cf_point_mlp1: unknown mode %d", mode);
     CF_REQUIRE(aligned16(d_feat) && aligned16(d_T), CF_ERR_ALIGN, "cf_point_mlp1: feat/T must be 16-byte aligned");
-    if (mode != CF_MODE_FP32_SIMT && d_workspace != nullptr) {
-        CF_REQUIRE(aligned16(d_workspace), CF_ERR_ALIGN, "cf_point_mlp1: workspace must be 16-byte aligned");
-        const int rc = point_mlp1_tc(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, mode, d_workspace,
-                                     (cudaStream_t)stream);
+    if (mode != CF_MODE_FP32_SIMT && (d_workspace != nullptr || d_packed != nullptr)) {
+        CF_REQUIRE(aligned16(d_workspace) && aligned16(d_packed), CF_ERR_ALIGN, "cf_point_mlp1: workspace / packed weights must be 16-byte aligned");
+        const int rc = point_mlp1_tc(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, mode, d_packed,
+                                     d_workspace, (cudaStream_t)stream);
         if (rc != CF_ERR_UNSUPPORTED) return rc;  // shapes without a tensor-core instantiation use the FFMA kernel
     }
     return point_mlp1_simt(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, (cudaStream_t)stream);

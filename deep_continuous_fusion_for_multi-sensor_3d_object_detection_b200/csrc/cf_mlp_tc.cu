@@ -458,9 +458,15 @@ struct Mlp1Params {
     int32_t tiles_per_frame;
 };
 
+template <int C>
+struct Mlp1Shape {
+    static constexpr int G = C <= 32 ? 1 : C <= 64 ? 2 : C == 96 || C == 192 ? 3 : 4;  // 128-thread groups per CTA
+};
+
 template <int C, int NS>
-__global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
+__global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const Mlp1Params p)
 {
+    constexpr int G = Mlp1Shape<C>::G, NT = kTile * G, NW = NT / 32;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -470,7 +476,8 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
     uint8_t *sA = smem + w_bytes;
     float *sb1 = reinterpret_cast<float *>(smem + w_bytes + a_bytes);
     float *swx = sb1 + C, *swy = swx + C, *swz = swy + C;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (kTile - 1), grp = tid / kTile;
     constexpr int kCols = C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
 
     if (tid == 0) {
@@ -479,20 +486,20 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
-    for (int c = tid; c < C; c += kThreads) {
+    for (int c = tid; c < C; c += NT) {
         const float *w = p.W1 + (size_t)c * (Ci + 3) + Ci;
         sb1[c] = __ldg(p.b1 + c);
         swx[c] = __ldg(w);
         swy[c] = __ldg(w + 1);
         swz[c] = __ldg(w + 2);
     }
-    copy_chunk<kThreads>(sW, p.wimg, w_bytes);
+    copy_chunk<NT>(sW, p.wimg, w_bytes);
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_acc = tmem_slot;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
     const uint32_t idesc = tc::make_idesc_bf16(kTile, C);
     const uint32_t sbo = kc_units * 128, lbo = 128;
@@ -504,13 +511,16 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
         const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
         const int32_t n_pts = valid_points(p.num_points, b, p.N);
         if (m0 >= n_pts) continue;  // uniform across the CTA
-        const int32_t m = m0 + tid;
-        const bool live = m < n_pts;
-        const float4 *frow = reinterpret_cast<const float4 *>(p.feat + ((size_t)b * p.N + (live ? m : m0)) * Ci);
-        for (int ku = 0; ku < kc_units; ++ku) {
+        // A tile: a warp takes one 8-row group x 4 operand units per step (coalesced 128-byte row segments in, 512
+        // contiguous bytes of the operand image out)
+        const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
+        for (int item = warp; item < 16 * (kc_units / 4); item += NW) {
+            const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
+            const int r = rg * 8 + (lane >> 2), ku = uq * 4 + (lane & 3);
             float v[8];
-            if (live) {
-                const float4 t0 = __ldg(frow + 2 * ku), t1 = __ldg(frow + 2 * ku + 1);
+            if (m0 + r < n_pts) {
+                const float4 *src = reinterpret_cast<const float4 *>(fb + (size_t)r * Ci + ku * 8);
+                const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
                 v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
             } else {
 #pragma unroll
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
             }
             uint4 hi, lo;
             tc::split_bf16x8(v, hi, lo, NS == 2);
-            const uint32_t off = tc::unit_offset(tid, ku, kc_units);
+            const uint32_t off = tc::unit_offset(r, ku, kc_units);
             *reinterpret_cast<uint4 *>(sA + off) = hi;
             if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Ci * 2 + off) = lo;
         }
@@ -545,6 +555,8 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
         tc::mbar_wait(&bar, phase);
         phase ^= 1u;
         tc::fence_after_sync();
+        const int32_t m = m0 + row;
+        const bool live = m < n_pts;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (live) {
             const float *q = p.points + ((size_t)b * p.N + m) * 3;
@@ -552,7 +564,7 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
         }
         __syncwarp();
 #pragma unroll 1
-        for (int cc = 0; cc < C / 32; ++cc) {
+        for (int cc = grp; cc < C / 32; cc += G) {
             float z[32];
             tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
             if (live) {
@@ -580,14 +592,15 @@ __global__ void __launch_bounds__(kThreads) k_point_mlp1_tc(const Mlp1Params p)
 template <int C, int NS>
 int launch_mlp1_tc(const Mlp1Params &p, cudaStream_t st)
 {
+    constexpr int NT = kTile * Mlp1Shape<C>::G;
     const int smem = NS * (C + kTile) * p.Ci * 2 + 4 * C * 4;
     CF_TRY(cuda_status(cudaFuncSetAttribute(k_point_mlp1_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                        "k_point_mlp1_tc smem attribute"));
     constexpr int kCols = C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
-    const int per_sm = std::max(1, std::min(std::min((227 * 1024) / (smem + 1024), 512 / kCols), 4));
+    const int per_sm = std::max(1, std::min(std::min((227 * 1024) / (smem + 1024), 512 / kCols), std::min(2048 / NT, 4)));
     const int64_t tiles = (int64_t)p.tiles_per_frame * p.B;
     const int64_t grid = std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
-    k_point_mlp1_tc<C, NS><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    k_point_mlp1_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
 
@@ -692,6 +705,20 @@ int launch_tc(const TcParams &p, cudaStream_t st)
 
 static size_t tc_weight_bytes(int32_t C, int NS) { return ((size_t)2 * NS * C * C * 2 + 255) / 256 * 256; }
 
+size_t fusion_tc_packed_bytes(int32_t C, int32_t mode) { return tc_weight_bytes(C, mode == CF_MODE_FP32 ? 2 : 1); }
+
+int fusion_tc_pack(const float *d_W2, const float *d_W3, int32_t C, int32_t mode, void *d_packed, cudaStream_t st)
+{
+    CF_REQUIRE(C % 32 == 0 && C >= 32 && C <= 256, CF_ERR_UNSUPPORTED, "cf_fusion_pack_weights: C=%d", C);
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    const int KC = kc_for(C, NS);
+    const int pack_blocks = (C * (C / 8) + 255) / 256;
+    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, (uint8_t *)d_packed);
+    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, (uint8_t *)d_packed + (size_t)NS * C * C * 2);
+    count_launches(2);
+    return launch_status("cf_fusion_pack_weights");
+}
+
 size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W)
 {
     const int NS = mode == CF_MODE_FP32 ? 2 : 1;
@@ -702,13 +729,14 @@ size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, 
 int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H,
               int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1, int32_t Ci,
               const float *d_W2, const float *d_b2, const float *d_W3, const float *d_b3, float *d_out, int32_t mode,
-              void *d_workspace, cudaStream_t st)
+              const void *d_packed, void *d_workspace, cudaStream_t st)
 {
     CF_REQUIRE(C % 32 == 0, CF_ERR_UNSUPPORTED, "cf_fusion_fwd: tensor-core path needs C %% 32 == 0 (C=%d)", C);
     const int NS = mode == CF_MODE_FP32 ? 2 : 1;
     const int KC = kc_for(C, NS);
-    uint8_t *img2 = (uint8_t *)d_workspace;
-    uint8_t *img3 = img2 + (size_t)NS * C * C * 2;
+    // packed W2 | W3 operand images: the caller's cached copy (cf_fusion_pack_weights) or packed here
+    const uint8_t *img2 = d_packed ? (const uint8_t *)d_packed : (const uint8_t *)d_workspace;
+    const uint8_t *img3 = img2 + (size_t)NS * C * C * 2;
     int32_t *cell_count = (int32_t *)((uint8_t *)d_workspace + tc_weight_bytes(C, NS));
     int32_t *cell_list = cell_count + 64;
     CF_REQUIRE(B <= 64, CF_ERR_ARG, "cf_fusion_fwd: batch %d > 64 frames per call", B);
@@ -722,9 +750,12 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
                                                                                             d_out, cell_list, cell_count);
         count_launches(1);
     }
-    const int pack_blocks = (C * (C / 8) + 255) / 256;
-    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, img2);
-    k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, img3);
+    if (!d_packed) {
+        const int pack_blocks = (C * (C / 8) + 255) / 256;
+        k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, (uint8_t *)d_workspace);
+        k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, (uint8_t *)d_workspace + (size_t)NS * C * C * 2);
+        count_launches(2);
+    }
     TcParams p;
     p.bev = d_bev; p.T = d_T; p.knn = d_knn; p.out = d_out; p.wimg2 = img2; p.wimg3 = img3; p.W1 = d_W1;
     p.b2 = d_b2; p.b3 = d_b3; p.B = B; p.N = N; p.H = H; p.W = W; p.K = K; p.Ci = Ci;
@@ -746,10 +777,19 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     }
 #undef CF_TC_CASE
     CF_TRY(rc);
-    count_launches(3);
+    count_launches(1);
     return launch_status("cf_fusion_fwd (tcgen05)");
 }
 
+
+int point_mlp1_tc_pack(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, cudaStream_t st)
+{
+    CF_REQUIRE(Ci % 16 == 0 && Ci <= 256 && C % 32 == 0, CF_ERR_UNSUPPORTED, "cf_point_mlp1_pack_weights: Ci=%d C=%d", Ci, C);
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    k_pack_weights<<<(C * (Ci / 8) + 255) / 256, 256, 0, st>>>(d_W1, C, Ci, Ci + 3, Ci, NS, (uint8_t *)d_packed);
+    count_launches(1);
+    return launch_status("cf_point_mlp1_pack_weights");
+}
 
 size_t point_mlp1_tc_workspace_bytes(int32_t Ci, int32_t C, int32_t mode)
 {
@@ -760,13 +800,16 @@ size_t point_mlp1_tc_workspace_bytes(int32_t Ci, int32_t C, int32_t mode)
 // returns CF_ERR_UNSUPPORTED (without setting an error) when the shape has no tensor-core instantiation
 int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
                   int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T, int32_t mode,
-                  void *d_workspace, cudaStream_t st)
+                  const void *d_packed, void *d_workspace, cudaStream_t st)
 {
     const int NS = mode == CF_MODE_FP32 ? 2 : 1;
     if (Ci % 16 != 0 || Ci > 256 || C % 32 != 0) return CF_ERR_UNSUPPORTED;
     if ((size_t)NS * (C + kTile) * Ci * 2 + 4 * C * 4 > 220 * 1024) return CF_ERR_UNSUPPORTED;
-    uint8_t *img = (uint8_t *)d_workspace;
-    k_pack_weights<<<(C * (Ci / 8) + 255) / 256, 256, 0, st>>>(d_W1, C, Ci, Ci + 3, Ci, NS, img);
+    const uint8_t *img = d_packed ? (const uint8_t *)d_packed : (const uint8_t *)d_workspace;
+    if (!d_packed) {
+        k_pack_weights<<<(C * (Ci / 8) + 255) / 256, 256, 0, st>>>(d_W1, C, Ci, Ci + 3, Ci, NS, (uint8_t *)d_workspace);
+        count_launches(1);
+    }
     Mlp1Params p;
     p.feat = d_feat; p.points = d_points; p.num_points = d_num_points; p.wimg = img; p.W1 = d_W1; p.b1 = d_b1; p.T = d_T;
     p.B = B; p.N = N; p.Ci = Ci; p.tiles_per_frame = (N + kTile - 1) / kTile;
@@ -781,7 +824,7 @@ int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_n
     }
 #undef CF_M1_CASE
     CF_TRY(rc);
-    count_launches(2);
+    count_launches(1);
     return launch_status("cf_point_mlp1 (tcgen05)");
 }
 

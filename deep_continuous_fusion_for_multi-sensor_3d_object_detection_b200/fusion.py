@@ -95,9 +95,11 @@ class _FusionFunction(torch.autograd.Function):
     """Forward = cf_point_mlp1 + cf_fusion_fwd.  Saves indices, inputs and weights, never the gathered rows."""
 
     @staticmethod
-    def forward(ctx, bev, feat, points, num_points, knn_idx, geom, mode, w1, b1, w2, b2, w3, b3):
-        T = ops.point_mlp1(feat, points, num_points, w1, b1, mode=mode)
-        out, _ = ops.fusion_fwd(bev, T, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode)
+    def forward(ctx, bev, feat, points, num_points, knn_idx, geom, mode, w1, b1, w2, b2, w3, b3, packed=None):
+        p1 = packed.w1(w1, mode) if packed is not None else None
+        p23 = packed.w23(w2, w3, mode) if packed is not None else None
+        T = ops.point_mlp1(feat, points, num_points, w1, b1, mode=mode, packed=p1)
+        out, _ = ops.fusion_fwd(bev, T, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode, packed=p23)
         ctx.save_for_backward(feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3)
         ctx.geom, ctx.mode = geom, mode
         return out
@@ -108,7 +110,7 @@ class _FusionFunction(torch.autograd.Function):
         gw1, gb1, gw2, gb2, gw3, gb3, gfeat = ops.fusion_bwd(grad_out, feat, points, num_points, knn_idx, ctx.geom, w1, b1,
                                                              w2, b2, w3)
         # d out / d bev is the identity
-        return grad_out, gfeat, None, None, None, None, None, gw1, gb1, gw2, gb2, gw3, gb3
+        return grad_out, gfeat, None, None, None, None, None, gw1, gb1, gw2, gb2, gw3, gb3, None
 
 
 class ContinuousFusion(nn.Module):
@@ -132,6 +134,7 @@ class ContinuousFusion(nn.Module):
         self.fc1 = nn.Linear(c_img + 3, c_bev)
         self.fc2 = nn.Linear(c_bev, c_bev)
         self.fc3 = nn.Linear(c_bev, c_bev)
+        self._packed = ops.PackedWeights()   # operand images of the weights, re-packed only when they change
 
     def extra_repr(self):
         return f"c_img={self.c_img}, c_bev={self.c_bev}, k={self.k}, radius={self.radius}, mode={self.mode}"
@@ -154,7 +157,7 @@ class ContinuousFusion(nn.Module):
         B, _, H, W = bev.shape
         knn_idx = frames.knn(H, W, geom, self.radius, self.k)
         args = (bev, frames.feat, frames.points, frames.num_points, knn_idx, geom, self.mode, self.fc1.weight,
-                self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias)
+                self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias, self._packed)
         needs_grad = torch.is_grad_enabled() and (bev.requires_grad or frames.feat.requires_grad or
                                                   any(p.requires_grad for p in self.parameters()))
         if needs_grad:

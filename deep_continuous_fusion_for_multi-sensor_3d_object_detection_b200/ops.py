@@ -127,7 +127,50 @@ def point_gather(img_feat, points, num_points, calib=None, uv=None, img_size=(64
     return out, workspace
 
 
-def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspace=None):
+class PackedWeights:
+    """Cache of the UMMA operand images of one layer's weights.  Re-packs only when a weight tensor was modified
+    in place (optimizer step -> Tensor._version changes) or replaced; in inference the weights are packed once."""
+
+    def __init__(self):
+        self._key1, self._buf1, self._key23, self._buf23 = None, None, None, None
+
+    @staticmethod
+    def _key(*tensors, mode):
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors) + (mode,)
+
+    def w1(self, W1, mode):
+        lib = load()
+        m = _lib.MODES[mode]
+        if m == _lib.MODE_SIMT:
+            return None
+        C_out, Ci = W1.shape[0], W1.shape[1] - 3
+        if Ci % 16 or Ci > 256 or C_out % 32:
+            return None
+        key = self._key(W1, mode=m)
+        if key != self._key1:
+            need = lib.cf_point_mlp1_workspace_bytes(Ci, C_out, m)
+            self._buf1 = torch.empty((need,), dtype=torch.uint8, device=W1.device)
+            check(lib.cf_point_mlp1_pack_weights(ptr(W1.detach().contiguous()), Ci, C_out, m, ptr(self._buf1), stream_ptr()),
+                  "cf_point_mlp1_pack_weights")
+            self._key1 = key
+        return self._buf1
+
+    def w23(self, W2, W3, mode):
+        lib = load()
+        m = _lib.MODES[mode]
+        Cc = W2.shape[0]
+        if m == _lib.MODE_SIMT or Cc % 32:
+            return None
+        key = self._key(W2, W3, mode=m)
+        if key != self._key23:
+            self._buf23 = torch.empty((lib.cf_fusion_packed_bytes(Cc, m),), dtype=torch.uint8, device=W2.device)
+            check(lib.cf_fusion_pack_weights(ptr(W2.detach().contiguous()), ptr(W3.detach().contiguous()), Cc, m,
+                                             ptr(self._buf23), stream_ptr()), "cf_fusion_pack_weights")
+            self._key23 = key
+        return self._buf23
+
+
+def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspace=None, packed=None):
     """K-4a.  T (B,N,C) = feat W1[:, :Ci]^T + points W1[:, Ci:]^T + b1."""
     lib = load()
     feat = _contig(feat, "feat", torch.float32, 3)
@@ -139,17 +182,17 @@ def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspac
     if W1.shape[1] != Ci + 3 or b1.shape[0] != C_out:
         raise ValueError(f"W1/b1: expected ({C_out},{Ci + 3})/({C_out},), got {tuple(W1.shape)}/{tuple(b1.shape)}")
     m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
-    need = lib.cf_point_mlp1_workspace_bytes(Ci, C_out, m)
+    need = 0 if packed is not None else lib.cf_point_mlp1_workspace_bytes(Ci, C_out, m)
     if need and (workspace is None or workspace.numel() < need):
         workspace = torch.empty((need,), dtype=torch.uint8, device=feat.device)
     if out is None:
         out = torch.empty((B, N, C_out), dtype=torch.float32, device=feat.device)
     check(lib.cf_point_mlp1(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, C_out, ptr(W1), ptr(b1), ptr(out), m,
-                            ptr(workspace) if need else None, stream_ptr()), "cf_point_mlp1")
+                            ptr(packed), ptr(workspace) if need else None, stream_ptr()), "cf_point_mlp1")
     return out
 
 
-def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None, workspace=None):
+def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None, workspace=None, packed=None):
     """K-4.  out = bev + W3 sum_k relu(W2 relu(T[idx_k] - e_cell) + b2) + n_valid b3."""
     lib = load()
     bev = _contig(bev, "bev", torch.float32, 4)
@@ -174,7 +217,8 @@ def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None,
         out = torch.empty_like(bev)
     x0, y0, dx, dy = [float(g) for g in geom]
     check(lib.cf_fusion_fwd(ptr(bev), ptr(T), ptr(knn_idx), B, N, Cc, H, W, K, x0, y0, dx, dy, ptr(W1), Ci, ptr(W2),
-                            ptr(b2), ptr(W3), ptr(b3), ptr(out), m, ptr(workspace), stream_ptr()), "cf_fusion_fwd")
+                            ptr(b2), ptr(W3), ptr(b3), ptr(out), m, ptr(packed), ptr(workspace), stream_ptr()),
+          "cf_fusion_fwd")
     return out, workspace
 
 

@@ -111,7 +111,14 @@ CF_API int cf_point_gather(const float *d_img_feat, int64_t sb, int64_t sc, int6
 CF_API size_t cf_point_mlp1_workspace_bytes(int32_t Ci, int32_t C, int32_t mode);
 CF_API int cf_point_mlp1(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
                   int32_t N, int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T,
-                  int32_t mode, void *d_workspace, void *stream);
+                  int32_t mode, const void *d_packed, void *d_workspace, void *stream);
+/* Optional: the tensor-core paths consume weights re-packed into the UMMA operand image.  A caller whose weights do
+ * not change between calls (inference) packs them once into a buffer of cf_point_mlp1_workspace_bytes /
+ * cf_fusion_packed_bytes bytes and passes it as d_packed; with d_packed == NULL every call packs into d_workspace. */
+CF_API int cf_point_mlp1_pack_weights(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, void *stream);
+CF_API size_t cf_fusion_packed_bytes(int32_t C, int32_t mode);
+CF_API int cf_fusion_pack_weights(const float *d_W2, const float *d_W3, int32_t C, int32_t mode, void *d_packed,
+                           void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K-4  per-neighbour MLP layers 1b/2/3 + K-sum-pool + BEV add for one scale (Appendix A9, A10);
@@ -125,7 +132,8 @@ CF_API size_t cf_fusion_workspace_bytes(int32_t C, int32_t mode, int32_t B, int3
 CF_API int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_knn_idx, int32_t B, int32_t N,
                   int32_t C, int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
                   const float *d_W1, int32_t Ci, const float *d_W2, const float *d_b2, const float *d_W3,
-                  const float *d_b3, float *d_out, int32_t mode, void *d_workspace, void *stream);
+                  const float *d_b3, float *d_out, int32_t mode, const void *d_packed, void *d_workspace,
+                  void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K-4b backward of cf_point_mlp1 + cf_fusion_fwd for one scale (training only).  d_gout = dL/d out (B,C,H,W);

@@ -304,22 +304,25 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                 // step: lane (r8 = lane/4, u = lane%4).  Global side: the 4 lanes of a row read one contiguous
                 // 128-byte segment of the point's T row; shared side: the warp's 32 units form 512 contiguous bytes of
                 // the operand image (conflict free).
-                const int items_per_slot = 16 * (kc_units / 4);
+                // NW is a multiple of the unit-quads per row, so a warp always works on the same 32 channels: its 16
+                // offset-weight values live in registers for the whole chunk (no shared-memory traffic per item)
+                constexpr int kQuads = kc_units / 4;
+                static_assert(NW % kQuads == 0, "warps per CTA must be a multiple of the unit quads per row");
+                const int uq = warp % kQuads, ku = uq * 4 + (lane & 3);
+                const int c0 = ch * KC + ku * 8;
+                const float4 x0 = *reinterpret_cast<const float4 *>(sw1x + c0);
+                const float4 x1 = *reinterpret_cast<const float4 *>(sw1x + c0 + 4);
+                const float4 y0 = *reinterpret_cast<const float4 *>(sw1y + c0);
+                const float4 y1 = *reinterpret_cast<const float4 *>(sw1y + c0 + 4);
 #pragma unroll 2
-                for (int item = warp; item < nb * items_per_slot; item += NW) {
-                    const int sl = item / items_per_slot, it = item - sl * items_per_slot;
-                    const int rg = it / (kc_units / 4), uq = it - rg * (kc_units / 4);
-                    const int r = rg * 8 + (lane >> 2), ku = uq * 4 + (lane & 3);
-                    const int c0 = ch * KC + ku * 8;
+                for (int it = warp / kQuads; it < nb * 16; it += NW / kQuads) {
+                    const int sl = it >> 4, rg = it & 15;
+                    const int r = rg * 8 + (lane >> 2);
                     const int32_t pr = sidx[r * K + k0 + sl];
                     const bool ok = pr >= 0;
                     const float cx = scx[r], cy = scy[r];
                     const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(ok ? pr : 0) * C + c0);
                     const float4 t0 = __ldg(trow), t1 = __ldg(trow + 1);
-                    const float4 x0 = *reinterpret_cast<const float4 *>(sw1x + c0);
-                    const float4 x1 = *reinterpret_cast<const float4 *>(sw1x + c0 + 4);
-                    const float4 y0 = *reinterpret_cast<const float4 *>(sw1y + c0);
-                    const float4 y1 = *reinterpret_cast<const float4 *>(sw1y + c0 + 4);
                     float v[8];
                     v[0] = fmaxf(t0.x - fmaf(x0.x, cx, y0.x * cy), 0.0f);
                     v[1] = fmaxf(t0.y - fmaf(x0.y, cx, y0.y * cy), 0.0f);

@@ -191,7 +191,7 @@ class GpuPipeline:
             frames = self.dcf.FrameContext(self.points if points is None else points,
                                            self.counts if counts is None else counts, self.grid)
             frames.gather(self.img if img is None else img, calib=self.calib, img_size=self.size)
-            return [layer(x, frames=frames) for layer, x in zip(self.layers, bev)]
+            return self.dcf.fuse_scales(frames, self.layers, bev)
 
     def timed_ops(self):
         """One step with a CUDA-event pair around every C-ABI call -> {op name: ms}, per-launch list."""
@@ -253,22 +253,36 @@ def run_gpu(args):
     lib = dcf.load()
 
     # ---- device-resident throughput -------------------------------------------------------------------
+    # The step is ~25 short launches on several streams; its host-side launch cost would otherwise be on the critical
+    # path, so after eager warm-up it is captured once into a CUDA graph and the timed region replays the graph.
     for _ in range(max(args.warmup, 3)):
         pipe.step()
+    torch.cuda.synchronize()
+    launches0 = lib.cf_launch_count()
+    pipe.step()
+    launches_per_step = lib.cf_launch_count() - launches0
+    graph = None
+    if not args.no_graph:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            pipe.step()
+        for _ in range(3):
+            graph.replay()
+    run_step = graph.replay if graph is not None else pipe.step
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = lib.cf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        pipe.step()
+        run_step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = lib.cf_launch_count() - launches0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: host buffers in, host buffers out ------------------------------------------------
@@ -285,35 +299,35 @@ def run_gpu(args):
     s_main = torch.cuda.current_stream(device)
 
     def e2e_step():
+        # frames are independent: stream them through one at a time, so that frame f+1 uploads while frame f computes
+        # and frame f-1 downloads (PCIe is full duplex; the three streams keep both directions busy)
         s_in.wait_stream(s_main)
+        staged = []
         with torch.cuda.stream(s_in):
-            pts = h_points.to(device, non_blocking=True)
-            cnt = h_counts.to(device, non_blocking=True)
-            img = h_img.to(device, non_blocking=True)
-            ev_frames = torch.cuda.Event()
-            ev_frames.record(s_in)
-            bev, ev_bev = [], []
-            for hb in h_bev:
-                bev.append(hb.to(device, non_blocking=True))
-                e = torch.cuda.Event()
-                e.record(s_in)
-                ev_bev.append(e)
-        s_main.wait_event(ev_frames)
+            for f in range(B):
+                pts = h_points[f:f + 1].to(device, non_blocking=True)
+                cnt = h_counts[f:f + 1].to(device, non_blocking=True)
+                img = h_img[f:f + 1].to(device, non_blocking=True)
+                bev = [hb[f:f + 1].to(device, non_blocking=True) for hb in h_bev]
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                staged.append((pts, cnt, img, bev, ev))
         with torch.no_grad():
-            frames = dcf.FrameContext(pts, cnt, pipe.grid)
-            frames.gather(img, calib=pipe.calib, img_size=pipe.size)
-            for layer, x, e, h in zip(pipe.layers, bev, ev_bev, h_out):
-                s_main.wait_event(e)
-                o = layer(x, frames=frames)
+            for f, (pts, cnt, img, bev, ev) in enumerate(staged):
+                s_main.wait_event(ev)
+                frames = dcf.FrameContext(pts, cnt, pipe.grid)
+                frames.gather(img, calib=pipe.calib, img_size=pipe.size)
+                outs = [layer(x, frames=frames) for layer, x in zip(pipe.layers, bev)]
                 done = torch.cuda.Event()
                 done.record(s_main)
                 s_out.wait_event(done)
                 with torch.cuda.stream(s_out):
-                    h.copy_(o, non_blocking=True)
-                o.record_stream(s_out)
-                x.record_stream(s_main)
-        for t in (pts, cnt, img):
-            t.record_stream(s_main)
+                    for o, h in zip(outs, h_out):
+                        h[f:f + 1].copy_(o, non_blocking=True)
+                for t in [pts, cnt, img] + bev:
+                    t.record_stream(s_main)
+                for o in outs:
+                    o.record_stream(s_out)
         s_main.wait_stream(s_out)
 
     e2e_steps = max(2, min(args.steps, 10))
@@ -379,7 +393,7 @@ def run_gpu(args):
         "config": {"workload": f"{args.workload}: BASELINE.json configs[1] (batch {B}/GPU, K={K}, "
                                f"{len(wl['scales'])} scales of a {wl['workload']['bev'][0]}x{wl['workload']['bev'][1]} BEV, "
                                f"~{int(n_valid)} LiDAR points/frame, 128x120x160 camera map)",
-                   "mlp_mode": mode, "frames_per_step_per_gpu": B, "l2_policy": "inputs_exceed_l2 (BEV in+out "
+                   "mlp_mode": mode, "frames_per_step_per_gpu": B, "launch": "eager" if graph is None else "cuda_graph_replay", "l2_policy": "inputs_exceed_l2 (BEV in+out "
                    f"{2 * sum(b.numel() * 4 for b in pipe.bev) / 1e6:.0f} MB per step vs 126 MB L2)"},
         "e2e": {"value": round(dcf.dist_util.aggregate_rate(B, world, e2e_steps, ms_e2e), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
@@ -434,6 +448,7 @@ def main():
     ap.add_argument("--mode", default=None, help="fp32 | bf16 | simt (default: the workload's)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--bucket-size", type=float, default=None, help="K-1 bucket pitch in metres (default: config)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -29,6 +29,8 @@ class FrameContext:
         self.feat = None
         self._gather_ws = None
         self._knn_cache = {}
+        self._tables = {}      # id(layer) -> (T, ready event): per-scale point tables computed ahead on side streams
+        self._streams = []
 
     def gather(self, img_feat, calib=None, uv=None, img_size=(640.0, 480.0)):
         if torch.is_grad_enabled() and img_feat.requires_grad:
@@ -59,6 +61,81 @@ class FrameContext:
                     return self._knn_cache[key]
         self._knn_cache[key] = ops.knn_query(self.bucket_start, self.sorted_pts, self.grid, H, W, geom, radius, K)
         return self._knn_cache[key]
+
+
+    # ------------------------------------------------------------------------------------------------------------
+    # Scheduling.  The per-scale point tables (K-4a) and the KNN tables (K-2) depend only on the frame, not on the BEV
+    # features, and the fusion of different scales is independent once its BEV map exists.  None of these launches
+    # fills the GPU on its own, so they are issued on side streams and joined with events: in the detector they run
+    # under the backbone's convolutions, in a stand-alone multi-scale call (fuse_scales) they overlap each other.
+    # ------------------------------------------------------------------------------------------------------------
+    def _side_streams(self, n):
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(self.points.device))
+        return self._streams[:n]
+
+    def precompute(self, layers, shapes=None):
+        """Launch the point tables of `layers` (and, if `shapes` = [(H,W)] is given, their KNN tables) ahead of use.
+        Inference only (no autograd through the tables)."""
+        if self.feat is None:
+            raise ValueError("FrameContext.precompute: call gather() first")
+        main = torch.cuda.current_stream(self.points.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        streams = self._side_streams(len(layers) + 1)
+        for layer, st in zip(layers, streams[1:]):
+            T = torch.empty((self.B, self.N, layer.c_bev), dtype=torch.float32, device=self.points.device)
+            packed = layer._packed.w1(layer.fc1.weight, layer.mode)   # packs on the current (main) stream if stale
+            st.wait_stream(main)
+            with torch.cuda.stream(st), torch.no_grad():
+                ops.point_mlp1(self.feat, self.points, self.num_points, layer.fc1.weight, layer.fc1.bias, mode=layer.mode,
+                               out=T, packed=packed)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            self._tables[id(layer)] = (T, ev)
+        if shapes is not None:
+            st = streams[0]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                for layer, (H, W) in zip(layers, shapes):
+                    knn = self.knn(H, W, layer.geom, layer.radius, layer.k)
+                    knn.record_stream(main)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            self._knn_ready = ev
+        return self
+
+    def table_for(self, layer):
+        """Precomputed point table of `layer` (waits for it on the current stream) or None."""
+        hit = self._tables.get(id(layer))
+        if hit is None:
+            return None
+        torch.cuda.current_stream(self.points.device).wait_event(hit[1])
+        return hit[0]
+
+    def wait_knn(self):
+        ev = getattr(self, "_knn_ready", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.points.device).wait_event(ev)
+
+
+def fuse_scales(frames, layers, bevs):
+    """Fuse several backbone scales of one batch at once (inference): tables and KNN ahead on side streams, then one
+    stream per scale, joined before returning.  Returns the fused maps in order."""
+    dev = frames.points.device
+    main = torch.cuda.current_stream(dev)
+    with torch.no_grad():
+        frames.precompute(layers, [tuple(b.shape[-2:]) for b in bevs])
+        frames.wait_knn()
+        outs = [torch.empty_like(b) for b in bevs]
+        streams = frames._side_streams(len(layers) + 1)[1:]
+        for layer, bev, out, st in zip(layers, bevs, outs, streams):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                layer(bev, frames=frames, out=out)
+        for st in streams:
+            main.wait_stream(st)
+    return outs
 
 
 def prepare_frames(points, num_points, img_feat, config=None, calib=None, uv=None, grid=None, img_size=None):
@@ -95,11 +172,13 @@ class _FusionFunction(torch.autograd.Function):
     """Forward = cf_point_mlp1 + cf_fusion_fwd.  Saves indices, inputs and weights, never the gathered rows."""
 
     @staticmethod
-    def forward(ctx, bev, feat, points, num_points, knn_idx, geom, mode, w1, b1, w2, b2, w3, b3, packed=None):
-        p1 = packed.w1(w1, mode) if packed is not None else None
+    def forward(ctx, bev, feat, points, num_points, knn_idx, geom, mode, w1, b1, w2, b2, w3, b3, packed=None, table=None,
+                out=None):
         p23 = packed.w23(w2, w3, mode) if packed is not None else None
-        T = ops.point_mlp1(feat, points, num_points, w1, b1, mode=mode, packed=p1)
-        out, _ = ops.fusion_fwd(bev, T, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode, packed=p23)
+        if table is None:
+            p1 = packed.w1(w1, mode) if packed is not None else None
+            table = ops.point_mlp1(feat, points, num_points, w1, b1, mode=mode, packed=p1)
+        out, _ = ops.fusion_fwd(bev, table, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode, packed=p23, out=out)
         ctx.save_for_backward(feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3)
         ctx.geom, ctx.mode = geom, mode
         return out
@@ -110,7 +189,7 @@ class _FusionFunction(torch.autograd.Function):
         gw1, gb1, gw2, gb2, gw3, gb3, gfeat = ops.fusion_bwd(grad_out, feat, points, num_points, knn_idx, ctx.geom, w1, b1,
                                                              w2, b2, w3)
         # d out / d bev is the identity
-        return grad_out, gfeat, None, None, None, None, None, gw1, gb1, gw2, gb2, gw3, gb3, None
+        return grad_out, gfeat, None, None, None, None, None, gw1, gb1, gw2, gb2, gw3, gb3, None, None, None
 
 
 class ContinuousFusion(nn.Module):
@@ -140,7 +219,7 @@ class ContinuousFusion(nn.Module):
         return f"c_img={self.c_img}, c_bev={self.c_bev}, k={self.k}, radius={self.radius}, mode={self.mode}"
 
     def forward(self, bev, img_feat=None, points=None, num_points=None, calib=None, uv=None, frames: FrameContext = None,
-                geom=None, return_knn: bool = False):
+                geom=None, return_knn: bool = False, out=None):
         geom = tuple(float(g) for g in geom) if geom is not None else self.geom
         if geom is None:
             raise ValueError("ContinuousFusion: BEV geometry (x0,y0,dx,dy) not set")
@@ -161,10 +240,11 @@ class ContinuousFusion(nn.Module):
         needs_grad = torch.is_grad_enabled() and (bev.requires_grad or frames.feat.requires_grad or
                                                   any(p.requires_grad for p in self.parameters()))
         if needs_grad:
-            out = _FusionFunction.apply(*args)
+            out = _FusionFunction.apply(*args, None, None)
         else:
             with torch.no_grad():
-                out = _FusionFunction.forward(_NullCtx(), *[a.detach() if isinstance(a, torch.Tensor) else a for a in args])
+                out = _FusionFunction.forward(_NullCtx(), *[a.detach() if isinstance(a, torch.Tensor) else a for a in args],
+                                              table=frames.table_for(self), out=out)
         return (out, knn_idx) if return_knn else out
 
 

@@ -222,6 +222,9 @@ class ObjectDetection_DCF(nn.Module):
             else:
                 frames.gather(img_feat, calib=self.calib, img_size=size)
 
+            if not torch.is_grad_enabled():
+                frames.precompute([self.fusion[f"group{g}"] for g in self.fusion_scales])
+
             def fuse(group, x):
                 key = f"group{group}"
                 return self.fusion[key](x, frames=frames) if key in self.fusion else x

@@ -350,12 +350,13 @@ def run_gpu(args):
         return
 
     # ---- per-kernel times + roofline of the dominant kernel (rank 0) -------------------------------------
-    reps = 5
+    reps = 7
     acc = {}
+    pipe.timed_ops()   # untimed: the graph capture emptied the allocator cache, the first pass re-populates it
     for _ in range(reps):
         for name, t_ms in pipe.timed_ops():
             acc.setdefault(name, []).append(t_ms)
-    per_op = {k: float(np.mean(v)) for k, v in acc.items()}
+    per_op = {k: float(np.median(v)) for k, v in acc.items()}
     step_ms = ms / args.steps
     dom = max(per_op, key=per_op.get)
     peak, peak_src = measured_peaks()

@@ -310,10 +310,13 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                 static_assert(NW % kQuads == 0, "warps per CTA must be a multiple of the unit quads per row");
                 const int uq = warp % kQuads, ku = uq * 4 + (lane & 3);
                 const int c0 = ch * KC + ku * 8;
-                const float4 x0 = *reinterpret_cast<const float4 *>(sw1x + c0);
-                const float4 x1 = *reinterpret_cast<const float4 *>(sw1x + c0 + 4);
-                const float4 y0 = *reinterpret_cast<const float4 *>(sw1y + c0);
-                const float4 y1 = *reinterpret_cast<const float4 *>(sw1y + c0 + 4);
+                // negated once, so that  T - (w1x cx + w1y cy)  is two FFMAs per channel
+                float nx[8], ny[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    nx[i] = -sw1x[c0 + i];
+                    ny[i] = -sw1y[c0 + i];
+                }
 #pragma unroll 2
                 for (int it = warp / kQuads; it < nb * 16; it += NW / kQuads) {
                     const int sl = it >> 4, rg = it & 15;
@@ -323,17 +326,14 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     const float cx = scx[r], cy = scy[r];
                     const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(ok ? pr : 0) * C + c0);
                     const float4 t0 = __ldg(trow), t1 = __ldg(trow + 1);
+                    const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
                     float v[8];
-                    v[0] = fmaxf(t0.x - fmaf(x0.x, cx, y0.x * cy), 0.0f);
-                    v[1] = fmaxf(t0.y - fmaf(x0.y, cx, y0.y * cy), 0.0f);
-                    v[2] = fmaxf(t0.z - fmaf(x0.z, cx, y0.z * cy), 0.0f);
-                    v[3] = fmaxf(t0.w - fmaf(x0.w, cx, y0.w * cy), 0.0f);
-                    v[4] = fmaxf(t1.x - fmaf(x1.x, cx, y1.x * cy), 0.0f);
-                    v[5] = fmaxf(t1.y - fmaf(x1.y, cx, y1.y * cy), 0.0f);
-                    v[6] = fmaxf(t1.z - fmaf(x1.z, cx, y1.z * cy), 0.0f);
-                    v[7] = fmaxf(t1.w - fmaf(x1.w, cx, y1.w * cy), 0.0f);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.0f;
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(nx[i], cx, fmaf(ny[i], cy, t[i])), 0.0f);
+                    if (!__all_sync(0xffffffffu, ok)) {  // rare after compaction: rows without a k-th neighbour
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.0f;
+                    }
                     uint4 hi, lo;
                     tc::split_bf16x8(v, hi, lo, NS == 2);
                     uint8_t *dst = sA + sl * L::kASlotBytes + tc::unit_offset(r, ku, kc_units);
@@ -373,7 +373,14 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         const float4 bb = *reinterpret_cast<const float4 *>(sb2 + cc * EW + i4 * 4);
                         const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) s[i4 * 4 + i] += valid ? fmaxf(z[i4 * 4 + i] + bq[i], 0.0f) : 0.0f;
+                        for (int i = 0; i < 4; ++i) z[i4 * 4 + i] = fmaxf(z[i4 * 4 + i] + bq[i], 0.0f);
+                    }
+                    if (__all_sync(0xffffffffu, valid)) {  // the common case after compaction: no mask needed
+#pragma unroll
+                        for (int i = 0; i < EW; ++i) s[i] += z[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < EW; ++i) s[i] += valid ? z[i] : 0.0f;
                     }
                 }
                 tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);

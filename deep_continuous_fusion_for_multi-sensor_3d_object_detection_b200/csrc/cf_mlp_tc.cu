@@ -58,6 +58,10 @@ __host__ __device__ constexpr int kc_for(int C, int NS)
 // A tiles and the resident weights still leave room for several CTAs per SM
 // launch shape of the two small-C instantiations (measured on B200, BASELINE configs[1]: several small CTAs per SM --
 // more independent tiles in flight -- beat fewer barrier rounds per tile; see profiles/README.md)
+#ifndef CF_ABUILD_UNROLL
+#define CF_ABUILD_UNROLL 2
+#endif
+constexpr int kAUnroll = CF_ABUILD_UNROLL;  // A-tile gather items in flight per warp
 #ifndef CF_SB32
 #define CF_SB32 1
 #define CF_SB64 1
@@ -301,14 +305,15 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             for (int ch = 0; ch < L::kChunks; ++ch) {
                 if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
                 // A chunk [128 rows x KC] per slot: a warp takes one 8-row group x 4 operand units (32 channels) per
-                // step: lane (r8 = lane/4, u = lane%4).  Global side: the 4 lanes of a row read one contiguous
-                // 128-byte segment of the point's T row; shared side: the warp's 32 units form 512 contiguous bytes of
-                // the operand image (conflict free).
+                // step: lane (r8 = lane%8, u = lane/8).  Global side: the 4 lanes of a row read one contiguous
+                // 128-byte segment of the point's T row; shared side: each quarter-warp (the unit of a 128-bit shared
+                // access) writes the 8 rows of one unit = 128 contiguous bytes of the operand image: conflict free.
+                // (lane/4, lane%4 would put 4 units x 128 B apart in one quarter-warp: a 4-way bank conflict.)
                 // NW is a multiple of the unit-quads per row, so a warp always works on the same 32 channels: its 16
                 // offset-weight values live in registers for the whole chunk (no shared-memory traffic per item)
                 constexpr int kQuads = kc_units / 4;
                 static_assert(NW % kQuads == 0, "warps per CTA must be a multiple of the unit quads per row");
-                const int uq = warp % kQuads, ku = uq * 4 + (lane & 3);
+                const int uq = warp % kQuads, ku = uq * 4 + (lane >> 3);
                 const int c0 = ch * KC + ku * 8;
                 // negated once, so that  T - (w1x cx + w1y cy)  is two FFMAs per channel
                 float nx[8], ny[8];
@@ -317,10 +322,10 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     nx[i] = -sw1x[c0 + i];
                     ny[i] = -sw1y[c0 + i];
                 }
-#pragma unroll 2
+#pragma unroll kAUnroll
                 for (int it = warp / kQuads; it < nb * 16; it += NW / kQuads) {
                     const int sl = it >> 4, rg = it & 15;
-                    const int r = rg * 8 + (lane >> 2);
+                    const int r = rg * 8 + (lane & 7);
                     const int32_t pr = sidx[r * K + k0 + sl];
                     const bool ok = pr >= 0;
                     const float cx = scx[r], cy = scy[r];
@@ -521,12 +526,12 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
         const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
         const int32_t n_pts = valid_points(p.num_points, b, p.N);
         if (m0 >= n_pts) continue;  // uniform across the CTA
-        // A tile: a warp takes one 8-row group x 4 operand units per step (coalesced 128-byte row segments in, 512
-        // contiguous bytes of the operand image out)
+        // A tile: a warp takes one 8-row group x 4 operand units per step, lane (r8 = lane%8, u = lane/8): coalesced
+        // 128-byte row segments in, and each quarter-warp writes 128 contiguous bytes of the operand image (conflict free)
         const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
         for (int item = warp; item < 16 * (kc_units / 4); item += NW) {
             const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
-            const int r = rg * 8 + (lane >> 2), ku = uq * 4 + (lane & 3);
+            const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
             float v[8];
             if (m0 + r < n_pts) {
                 const float4 *src = reinterpret_cast<const float4 *>(fb + (size_t)r * Ci + ku * 8);

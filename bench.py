@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+CONFIG_OF = {"cfg0": "configs[0]", "cfg1": "configs[1]", "cfg2": "configs[2]", "yaml": "reference YAML grid"}
 METRIC = "fusion_layer_frames_per_sec"
 UNIT = "frames/s"
 
@@ -376,6 +377,26 @@ def run_gpu(args):
                 "traffic": None, "peak_source": peak_src, "ms_per_launch": round(per_op[dom], 4),
                 "share_of_step": round(per_op[dom] / sum(per_op.values()), 3),
                 "note": "dominant kernel is compute/latency bound; see DESIGN.md"}
+    # ---- rotated-box post-process beside it: Test.NMS_SAT semantics on 2 000 boxes per frame ----------------
+    nms = None
+    try:
+        boxes_h = np.stack([dcf.synthetic.nms_boxes(500 + f, 2000) for f in range(B)])
+        boxes_d = torch.zeros((B, 2048, 7), device=device)
+        boxes_d[:, :2000] = torch.from_numpy(boxes_h).to(device)
+        counts_d = torch.full((B,), 2000, dtype=torch.int32, device=device)
+        for _ in range(3):
+            keep, kcnt = dcf.ops.nms_sat(boxes_d, counts_d)
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(10):
+            keep, kcnt = dcf.ops.nms_sat(boxes_d, counts_d)
+        n1.record()
+        torch.cuda.synchronize()
+        nms_ms = n0.elapsed_time(n1) / 10
+        nms = {"boxes_per_frame": 2000, "frames": B, "ms_per_call": round(nms_ms, 4),
+               "frames_per_sec": round(B / (nms_ms * 1e-3), 1), "kept_per_frame": [int(x) for x in kcnt.tolist()]}
+    except Exception as e:  # never let the side measurement break the bench line
+        nms = {"error": str(e)[:200]}
     n_valid = float(np.mean(wl["num_points"]))
     layer_bytes = algorithmic_bytes_per_frame(wl, wl["img_feat"].shape[1], wl["img_feat"].shape[2:], n_valid)
     layer_gbs = layer_bytes * B / (step_ms * 1e-3) / 1e9
@@ -391,7 +412,7 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if mode in ("fp32", "simt") else "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: BASELINE.json configs[1] (batch {B}/GPU, K={K}, "
+        "config": {"workload": f"{args.workload}: BASELINE.json {CONFIG_OF.get(args.workload, 'custom')} (batch {B}/GPU, K={K}, "
                                f"{len(wl['scales'])} scales of a {wl['workload']['bev'][0]}x{wl['workload']['bev'][1]} BEV, "
                                f"~{int(n_valid)} LiDAR points/frame, 128x120x160 camera map)",
                    "mlp_mode": mode, "frames_per_step_per_gpu": B, "launch": "eager" if graph is None else "cuda_graph_replay", "l2_policy": "inputs_exceed_l2 (BEV in+out "
@@ -403,6 +424,7 @@ def run_gpu(args):
         "layer": {"algorithmic_bytes_per_frame": layer_bytes, "achieved_gbs": round(layer_gbs, 1),
                   "frac_of_hbm_peak": round(layer_gbs / peak, 4)},
         "kernel_ms": {k: round(v, 4) for k, v in per_op.items()},
+        "nms_sat": nms,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
@@ -433,7 +455,8 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": max(args.warmup, 0),
             "ms_per_step": round(1e3 * B / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: BASELINE.json configs[1]", "frames_per_step_per_gpu": B},
+            "config": {"workload": f"{args.workload}: BASELINE.json {CONFIG_OF.get(args.workload, 'custom')}",
+                       "frames_per_step_per_gpu": B},
             "cpu_baseline": {"value": round(v, 6), "unit": UNIT, "cores": nthr, "kind": "port", "sample": desc},
             "e2e": {"value": round(v, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -2,25 +2,34 @@
 // the BEV add for one backbone scale, fused so that neither the gathered rows nor the hidden activations
 // ever leave the SM.
 //
-// Tile = 128 consecutive BEV cells (= the M of a cta_group::1 UMMA, one TMEM lane per cell).  Per tile:
+// Tile = 128 BEV cells (= the M of a cta_group::1 UMMA, one TMEM lane per cell) taken from the compacted list of
+// cells that have at least one neighbour.  Per tile:
 //   for each neighbour slot k:
 //     A_k[128 x C]  = relu(T[idx_k] - e_cell)            built by CUDA cores straight into shared memory in the
 //                                                         UMMA operand layout, bf16 (+ bf16 residual in fp32 mode)
-//     acc[128 x C]  = A_k * W2^T                          tcgen05.mma, accumulator in TMEM
-//     pooled       += valid ? relu(acc + b2) : 0          tcgen05.ld -> registers -> tcgen05.st (pooled lives in TMEM)
-//   acc = pooled * W3^T                                   tcgen05.mma
-//   out = bev + acc + n_valid * b3                        epilogue: coalesced NCHW read of bev, write of out
-// Slots for which no cell of the tile has a neighbour are skipped (most far-field tiles skip everything).
+//     acc[128 x C]  = valid_k * b2 + A_k * W2^T           tcgen05.mma, accumulator in TMEM; the bias rides on an extra
+//                                                         K=16 step whose A column is the row's valid flag, so rows
+//                                                         without a k-th neighbour come out as exactly 0
+//     pooled       += relu(acc)                           tcgen05.ld -> registers -> tcgen05.st (pooled lives in TMEM)
+//   acc = n_valid * b3 + pooled * W3^T                    tcgen05.mma (bias column = the row's neighbour count)
+//   out = bev + acc                                       epilogue: coalesced NCHW read of bev, write of out
+// The same CTAs also copy bev -> out for the cells WITHOUT a neighbour (the other end of the compacted list), so the
+// memory-bound copy overlaps the issue-bound MLP tiles of the CTAs that share the SM.
+//
+// Instruction diet of the two per-(neighbour, channel) loops (they bound the kernel, not HBM or the tensor pipe):
+//   operand build  T - (w1x cx + w1y cy): two FFMA2 per channel PAIR; ReLU folded into the bf16 conversions
+//                  (cvt.rz.relu / cvt.rn.relu), hi/lo residual with one FADD2 per pair
+//   slot epilogue  relu + pooled add: FMNMX + half a FADD2 per channel; no bias add, no valid-mask select
 //
 // Precision modes
 //   CF_MODE_BF16: operands rounded to bf16, fp32 accumulate (tolerance 1e-2, Appendix A12).
-//   CF_MODE_FP32: every fp32 operand x is split into bf16 hi + bf16 lo (x ~ hi + lo to 2^-17); the product is
-//                 hi*hi + hi*lo + lo*hi, three MMAs into the same fp32 accumulator: relative error ~2^-16 per
+//   CF_MODE_FP32: every fp32 operand x is split into bf16 hi + bf16 lo (x ~ hi + lo to 2^-16); the product is
+//                 hi*hi + hi*lo + lo*hi, three MMAs into the same fp32 accumulator: relative error ~2^-15 per
 //                 product, which keeps the fused features within 1e-4 of the fp32 oracle.
 //
 // Weights are pre-packed once per call (k_pack_weights) into the shared-memory operand image, chunked along K;
-// when a whole layer fits they stay resident in shared memory for the life of the CTA, otherwise (C >= 192 in
-// fp32 mode, C = 256) chunks of 64 input channels are streamed from L2 per use.
+// up to C = 128 both layers stay resident in shared memory for the life of the CTA, above that chunks of 64 input
+// channels are streamed from L2 per use.
 #include "cf_common.cuh"
 #include "cf_tcgen05.cuh"
 
@@ -44,40 +53,44 @@ struct TcParams {
     int32_t B, N, H, W, K, Ci;
     float x0, y0, dx, dy;
     int64_t tiles_per_frame, tiles_total;
-    const int32_t *cell_list;   // (B, cells) compacted indices of the cells that have at least one neighbour
-    const int32_t *cell_count;  // (B)
+    // (B, cells) per frame: indices of the cells that have a neighbour from the front, the others from the back
+    const int32_t *cell_list;
+    const int32_t *cell_count;  // (B) number of cells with a neighbour
+    int32_t copy_dead;          // this kernel copies bev -> out for the cells without a neighbour
 };
 
 __host__ __device__ constexpr int kc_for(int C, int NS)
 {
     // resident when both layers' packed weights + the A tile fit in shared memory, else stream 64-wide chunks
-    return (NS == 1 ? (C <= 192) : (C <= 128)) ? C : 64;
+    return C <= 128 ? C : 64;
 }
 
-// neighbour slots processed per barrier round (each has its own A tile and TMEM accumulator); > 1 only where the
-// A tiles and the resident weights still leave room for several CTAs per SM
+#ifndef CF_GATHER_BATCH
+#define CF_GATHER_BATCH 4
+#endif
+constexpr int kGatherBatch = CF_GATHER_BATCH;  // neighbour-row gathers in flight per lane
 // launch shape of the two small-C instantiations (measured on B200, BASELINE configs[1]: several small CTAs per SM --
 // more independent tiles in flight -- beat fewer barrier rounds per tile; see profiles/README.md)
-#ifndef CF_ABUILD_UNROLL
-#define CF_ABUILD_UNROLL 2
-#endif
-constexpr int kAUnroll = CF_ABUILD_UNROLL;  // A-tile gather items in flight per warp
-#ifndef CF_SB32
-#define CF_SB32 1
-#define CF_SB64 1
+#ifndef CF_G32
 #define CF_G32 1
 #define CF_G64 2
-#define CF_EW32 16
-#define CF_EW64 16
-#define CF_MB32 6
+#define CF_MB32 5
 #define CF_MB64 3
 #endif
-__host__ __device__ constexpr int slots_per_round(int C, int NS) { return C <= 32 ? CF_SB32 : (C <= 64 ? CF_SB64 : (NS == 1 && C <= 128 ? 2 : 1)); }
 
 __host__ __device__ constexpr int tmem_cols_for(int cols)
 {
     return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
 }
+
+constexpr int kEW = 16;  // TMEM columns per epilogue step
+
+// the "row" a cell without a k-th neighbour gathers: relu(-1e30 - e) = 0, so the operand build needs no select
+#define CF_NEG8 -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f
+#define CF_NEG64 CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8
+__device__ float g_neg_row[256] = {CF_NEG64, CF_NEG64, CF_NEG64, CF_NEG64};
+#undef CF_NEG64
+#undef CF_NEG8
 
 template <int C, int NS>
 struct TcLayout {
@@ -87,17 +100,19 @@ struct TcLayout {
     static_assert(C % KC == 0 && KC % 32 == 0, "channel count must be a multiple of the K-chunk");
     static constexpr int kWChunkBytes = NS * C * KC * 2;            // one K-chunk of one layer, all splits
     static constexpr int kWBytes = kResident ? 2 * kWChunkBytes : kWChunkBytes;
-    static constexpr int SB = kResident ? slots_per_round(C, NS) : 1;
-    static constexpr int kASlotBytes = NS * kTile * KC * 2;         // one A tile (all splits)
-    static constexpr int kABytes = SB * kASlotBytes;
+    static constexpr int kABytes = NS * kTile * KC * 2;             // one A tile (all splits)
     static constexpr int kOffA = kWBytes;
-    static constexpr int kOffF = kOffA + kABytes;                   // floats: b2, b3, w1x, w1y
-    static constexpr int kOffIdx = kOffF + 4 * C * 4;               // int32 [128][CF_MAX_K]
-    static constexpr int kOffCtr = kOffIdx + kTile * CF_MAX_K * 4;  // float cx[128], cy[128]
-    static constexpr int kOffCell = kOffCtr + 2 * kTile * 4;        // int32 cell index of each row
-    static constexpr int kOffBar = kOffCell + kTile * 4;            // mbarrier (8 B) + tmem ptr (4 B)
-    static constexpr int kSmemBytes = kOffBar + 16;
-    static constexpr int kTmemCols = tmem_cols_for((SB + 1) * C);   // SB accumulators + the pooled sum
+    static constexpr int kOffAb = kOffA + kABytes;                  // bias A operand: 128 rows x 16 bf16 (2 units / row)
+    static constexpr int kAbBytes = kTile * 32;
+    static constexpr int kOffWb = kOffAb + kAbBytes;                // bias B operands: 2 layers x (C rows x 16 bf16)
+    static constexpr int kWbBytes = C * 32;
+    static constexpr int kOffCtr = kOffWb + 2 * kWbBytes;           // float4 (cx,cx,cy,cy) [2][128]
+    static constexpr int kOffW1 = kOffCtr + 2 * kTile * 16;         // float w1x[C], w1y[C]
+    static constexpr int kOffBar = kOffW1 + 2 * C * 4;              // mbarrier (8 B), tmem ptr (4 B), pad, int wmax[2][4]
+    static constexpr int kOffIdx = kOffBar + 48;                    // int32 [2][K][128] (K known at launch)
+    static __host__ __device__ constexpr int smem_bytes(int K) { return kOffIdx + 2 * K * kTile * 4; }
+    static constexpr int kTmemCols = tmem_cols_for(2 * C);          // accumulator + the pooled sum
+    static_assert(smem_bytes(CF_MAX_K) <= 227 * 1024, "layout exceeds the shared memory of an SM");
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -157,51 +172,54 @@ __device__ __forceinline__ void issue_chunk(uint32_t a_addr, uint32_t w_addr, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Cell compaction.  Only ~1/3 of the BEV cells of a LiDAR frame have a point within the radius.  This pass
-//   * appends the index of every cell with a neighbour to a per-frame list (block-local order, one atomicAdd per
-//     block, so the list is a concatenation of ascending runs: neighbouring list entries are neighbouring cells and
-//     the fused kernel's BEV accesses stay coalesced), and
-//   * finishes the cells WITHOUT a neighbour right here: out = bev (skipped when the layer runs in place).
+// Cell compaction.  Only ~1/3 of the BEV cells of a LiDAR frame have a point within the radius.  This pass splits
+// the cells of each frame into two lists that share one array of `cells` ints: cells WITH a neighbour from the front,
+// cells WITHOUT one from the back (block-local order, one atomicAdd per block and list, so each list is a
+// concatenation of ascending runs: neighbouring list entries are neighbouring cells and the fused kernel's BEV
+// accesses stay coalesced).  count[b] = cells with a neighbour, count[64 + b] = cells without.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cell_compact(const int32_t *__restrict__ knn, int32_t K, int64_t cells, int32_t C,
-                                                      const float *__restrict__ bev, float *__restrict__ out,
+__global__ void __launch_bounds__(256) k_cell_compact(const int32_t *__restrict__ knn, int32_t K, int64_t cells,
                                                       int32_t *__restrict__ list, int32_t *__restrict__ count)
 {
-    __shared__ int32_t warp_excl[8];
-    __shared__ int32_t base;
+    __shared__ int32_t warp_live[8], warp_dead[8];
+    __shared__ int32_t base_live, base_dead;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t cell = (int64_t)blockIdx.x * 256 + tid;
     const bool inside = cell < cells;
     const bool live = inside && __ldg(knn + ((size_t)b * cells + cell) * K) >= 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, live);
-    if (lane == 0) warp_excl[warp] = __popc(bal);
+    const bool dead = inside && !live;
+    const unsigned bal_live = __ballot_sync(0xffffffffu, live), bal_dead = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) {
+        warp_live[warp] = __popc(bal_live);
+        warp_dead[warp] = __popc(bal_dead);
+    }
     __syncthreads();
     if (tid == 0) {
-        int32_t run = 0;
+        int32_t run_l = 0, run_d = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
-            const int32_t c = warp_excl[w];
-            warp_excl[w] = run;
-            run += c;
+            const int32_t cl = warp_live[w], cd = warp_dead[w];
+            warp_live[w] = run_l;
+            warp_dead[w] = run_d;
+            run_l += cl;
+            run_d += cd;
         }
-        base = run ? atomicAdd(count + b, run) : 0;
+        base_live = run_l ? atomicAdd(count + b, run_l) : 0;
+        base_dead = run_d ? atomicAdd(count + 64 + b, run_d) : 0;
     }
     __syncthreads();
-    if (live) list[(size_t)b * cells + base + warp_excl[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)cell;
-    if (inside && !live && out != bev) {
-        const size_t o = (size_t)b * C * cells + cell;
-#pragma unroll 8
-        for (int c = 0; c < C; ++c) out[o + (size_t)c * cells] = __ldg(bev + o + (size_t)c * cells);
-    }
+    const unsigned below = (1u << lane) - 1u;
+    int32_t *fl = list + (size_t)b * cells;
+    if (live) fl[base_live + warp_live[warp] + __popc(bal_live & below)] = (int32_t)cell;
+    if (dead) fl[cells - 1 - (base_dead + warp_dead[warp] + __popc(bal_dead & below))] = (int32_t)cell;
 }
 
 // Thread layout: G groups of 128 threads.  Thread (row = tid % 128, grp = tid / 128) owns BEV cell `row` of the
-// tile; the G threads of a row split the 16-byte operand units of the A tile and the EW-column chunks of the
+// tile; the G threads of a row split the 16-byte operand units of the A tile and the 16-column chunks of the
 // epilogues between them (warp w may only touch TMEM lanes 32*(w%4)..+31, which is exactly its rows).
 template <int C>
 struct TcShape {
     static constexpr int G = C <= 32 ? CF_G32 : C <= 64 ? CF_G64 : C == 96 || C == 192 ? 3 : 4;
-    static constexpr int EW = C <= 32 ? CF_EW32 : C <= 64 ? CF_EW64 : 32;
     static constexpr int kMinBlocks = C <= 32 ? CF_MB32 : C <= 64 ? CF_MB64 : 1;
 };
 
@@ -209,24 +227,24 @@ template <int C, int NS>
 __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks) k_fusion_tc(const TcParams p)
 {
     using L = TcLayout<C, NS>;
-    constexpr int G = TcShape<C>::G, EW = TcShape<C>::EW;
+    constexpr int G = TcShape<C>::G, EW = kEW;
     constexpr int NT = kTile * G;
     constexpr int KC = L::KC;
     constexpr int kc_units = KC / 8;
     constexpr int kChunksE = C / EW;  // epilogue chunks over all C columns
+    static_assert(C % G == 0 && (C / G) % 8 == 0, "column split between the thread groups");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sW = smem;
     uint8_t *sA = smem + L::kOffA;
-    float *sb2 = reinterpret_cast<float *>(smem + L::kOffF);
-    float *sb3 = sb2 + C;
-    float *sw1x = sb3 + C;
+    uint8_t *sAb = smem + L::kOffAb;
+    uint8_t *sWb = smem + L::kOffWb;
+    float4 *sctr = reinterpret_cast<float4 *>(smem + L::kOffCtr);
+    float *sw1x = reinterpret_cast<float *>(smem + L::kOffW1);
     float *sw1y = sw1x + C;
-    int32_t *sidx = reinterpret_cast<int32_t *>(smem + L::kOffIdx);
-    float *scx = reinterpret_cast<float *>(smem + L::kOffCtr);
-    float *scy = scx + kTile;
-    int32_t *scell = reinterpret_cast<int32_t *>(smem + L::kOffCell);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8);
+    int32_t *swmax = reinterpret_cast<int32_t *>(smem + L::kOffBar + 16);   // [2][4]
+    int32_t *sidx = reinterpret_cast<int32_t *>(smem + L::kOffIdx);         // [2][K][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), grp = tid / kTile;
@@ -242,160 +260,217 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(tmem_slot, L::kTmemCols);
     for (int c = tid; c < C; c += NT) {
-        sb2[c] = __ldg(p.b2 + c);
-        sb3[c] = __ldg(p.b3 + c);
         sw1x[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci);
         sw1y[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci + 1);
+    }
+    // bias operands.  A side (rewritten per round): row r, k-columns 0 and 1 = the row's flag, the other 14 stay 0.
+    // B side: row n = (hi(b[n]), lo(b[n]), 0 ...), so flag * (hi + lo) lands in the accumulator with one K=16 step.
+    for (int o = tid * 16; o < L::kAbBytes + 2 * L::kWbBytes; o += NT * 16) *reinterpret_cast<uint4 *>(sAb + o) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int n = tid; n < 2 * C; n += NT) {
+        const int layer = n / C, c = n - layer * C;
+        const float bv = __ldg((layer ? p.b3 : p.b2) + c);
+        const __nv_bfloat16 h = __float2bfloat16_rn(bv);
+        const __nv_bfloat16 l = __float2bfloat16_rn(bv - __bfloat162float(h));
+        const uint32_t packed = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+        *reinterpret_cast<uint32_t *>(sWb + layer * L::kWbBytes + tc::unit_offset(c, 0, 2)) = packed;
     }
     if (L::kResident) {
         copy_chunk<NT>(sW, p.wimg2, L::kWChunkBytes);
         copy_chunk<NT>(sW + L::kWChunkBytes, p.wimg3, L::kWChunkBytes);
-        tc::fence_proxy_async();
     }
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr int SB = L::SB;
-    const uint32_t tmem_acc = tmem_base;                                // SB accumulators: columns [s*C, (s+1)*C)
-    const uint32_t tmem_pool = tmem_base + SB * C;                      // pooled sum: columns [SB*C, (SB+1)*C)
+    const uint32_t tmem_acc = tmem_base;                                // accumulator: columns [0, C)
+    const uint32_t tmem_pool = tmem_base + C;                           // pooled sum:  columns [C, 2C)
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;        // this warp's TMEM lanes == its rows
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
-    uint32_t phase = 0;
+    const uint32_t sAb_addr = tc::smem_u32(sAb), sWb_addr = tc::smem_u32(sWb);
+    const uint32_t sidx_addr = tc::smem_u32(sidx), sctr_addr = tc::smem_u32(sctr);
+    uint32_t *ab_row = reinterpret_cast<uint32_t *>(sAb + tc::unit_offset(row, 0, 2));
+    constexpr uint32_t idesc = tc::make_idesc_bf16(kTile, C);
+    uint32_t phase = 0, iter = 0;
+
+    // A-tile work split: a warp takes one 8-row group x 4 operand units (32 channels) per step, lane (r8 = lane % 8,
+    // u = lane / 8).  Global side: the 4 lanes of a row read one contiguous 128-byte segment of the point's T row;
+    // shared side: each quarter-warp (the unit of a 128-bit shared access) writes the 8 rows of one unit = 128 contiguous
+    // bytes of the operand image: conflict free.  NW is a multiple of the unit-quads per row, so a warp always works on
+    // the same 32 channels of a chunk and its negated offset weights stay in registers.
+    constexpr int kQuads = kc_units / 4;
+    static_assert(NW % kQuads == 0, "warps per CTA must be a multiple of the unit quads per row");
+    const int ku = (warp % kQuads) * 4 + (lane >> 3);
+    const int r8 = lane & 7;
+    float2 nx[4], ny[4];   // -(w1x, w1y) of this lane's 8 channels:  T - (w1x cx + w1y cy) = two FFMA2 per channel pair
+    auto load_offset_weights = [&](int ch) {
+        const int c0 = ch * KC + ku * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            nx[i] = make_float2(-sw1x[c0 + 2 * i], -sw1x[c0 + 2 * i + 1]);
+            ny[i] = make_float2(-sw1y[c0 + 2 * i], -sw1y[c0 + 2 * i + 1]);
+        }
+    };
+    if (L::kChunks == 1) load_offset_weights(0);
 
     for (int64_t tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-        // tiles run over the COMPACTED list of cells that have a neighbour (k_cell_compact); cells without one were
-        // already copied bev -> out by that pass, so every row built below is (almost always) useful work
         const int b = (int)(tile / p.tiles_per_frame);
         const int64_t e0 = (tile - (int64_t)b * p.tiles_per_frame) * kTile;
         const int32_t n_live = p.cell_list ? __ldg(p.cell_count + b) : (int32_t)cells;  // no list: every cell, in order
+        // ---- cells without a neighbour (back of the list): out = bev ---------------------------------------------------
+        if (p.copy_dead) {
+            const int64_t j = e0 + row;
+            if (j < cells - n_live) {
+                const int32_t dc = __ldg(p.cell_list + (size_t)b * cells + (cells - 1 - j));
+                constexpr int CG = C / G;
+                const size_t o = ((size_t)b * C + grp * CG) * cells + dc;
+#pragma unroll 1
+                for (int c = 0; c < CG; c += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __ldcs(p.bev + o + (size_t)(c + i) * cells);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) __stcs(p.out + o + (size_t)(c + i) * cells, v[i]);
+                }
+            }
+        }
         if (e0 >= n_live) continue;  // uniform
+        // ---- tile header: cell, centre, neighbour indices (slot-major in shared memory), rounds of the tile ------------
+        const int par = iter & 1;
+        ++iter;
         const bool in_range = e0 + row < n_live;
         const int32_t cell = !in_range ? 0 : p.cell_list ? __ldg(p.cell_list + (size_t)b * cells + e0 + row) : (int32_t)(e0 + row);
-        if (tid < kTile) {
+        int32_t *sidx_t = sidx + par * K * kTile;
+        int n_valid = 0;
+        {
+            const int32_t *kr = p.knn + ((size_t)b * cells + cell) * K;
+            for (int k = 0; k < K; ++k) {
+                const int32_t v = in_range ? __ldg(kr + k) : -1;
+                n_valid += v >= 0;
+                if (grp == 0) sidx_t[k * kTile + row] = v;
+            }
+        }
+        if (grp == 0) {
             float cx = 0.f, cy = 0.f;
             if (in_range) {
                 const int32_t i = cell / p.W, j = cell - i * p.W;
                 cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
                 cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
             }
-            scx[row] = cx;
-            scy[row] = cy;
-            scell[row] = in_range ? cell : -1;
+            sctr[par * kTile + row] = make_float4(cx, cx, cy, cy);
+            const int wm = __reduce_max_sync(0xffffffffu, n_valid);
+            if (lane == 0) swmax[par * 4 + warp] = wm;
         }
         __syncthreads();
-        // neighbour indices of the tile's cells (K consecutive ints per cell; list entries are mostly consecutive cells)
-        for (int i = tid; i < kTile * K; i += NT) {
-            const int r = i / K, kk = i - r * K;
-            const int32_t cr = scell[r];
-            sidx[i] = cr >= 0 ? __ldg(p.knn + ((size_t)b * cells + cr) * K + kk) : -1;
+        // slots are sorted (empty ones form a suffix): the tile needs as many rounds as its best-connected cell
+        int R;
+        {
+            const int4 wm = *reinterpret_cast<const int4 *>(swmax + par * 4);
+            R = max(max(wm.x, wm.y), max(wm.z, wm.w));
         }
-        __syncthreads();
+        const float4 *sctr_t = sctr + par * kTile;
         const float *Tb = p.T + (size_t)b * p.N * C;
-        int n_valid = 0;
-        for (int k = 0; k < K; ++k) n_valid += sidx[row * K + k] >= 0;
-        bool pooled_live = false;  // uniform across the CTA
 
-        // neighbour slots in rounds of SB: build SB A tiles, ONE barrier, SB MMA groups, ONE commit / wait, one epilogue
-        for (int k0 = 0; k0 < K; k0 += SB) {
-            const int nb = min(SB, K - k0);
-            // slots are sorted (empty ones form a suffix): if nobody has a k0-th neighbour, nobody has a later one
-            if (!__syncthreads_or(sidx[row * K + k0] >= 0)) break;
-
+        for (int k = 0; k < R; ++k) {
+            const int32_t *sidx_k = sidx_t + k * kTile;
             for (int ch = 0; ch < L::kChunks; ++ch) {
                 if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
-                // A chunk [128 rows x KC] per slot: a warp takes one 8-row group x 4 operand units (32 channels) per
-                // step: lane (r8 = lane%8, u = lane/8).  Global side: the 4 lanes of a row read one contiguous
-                // 128-byte segment of the point's T row; shared side: each quarter-warp (the unit of a 128-bit shared
-                // access) writes the 8 rows of one unit = 128 contiguous bytes of the operand image: conflict free.
-                // (lane/4, lane%4 would put 4 units x 128 B apart in one quarter-warp: a 4-way bank conflict.)
-                // NW is a multiple of the unit-quads per row, so a warp always works on the same 32 channels: its 16
-                // offset-weight values live in registers for the whole chunk (no shared-memory traffic per item)
-                constexpr int kQuads = kc_units / 4;
-                static_assert(NW % kQuads == 0, "warps per CTA must be a multiple of the unit quads per row");
-                const int uq = warp % kQuads, ku = uq * 4 + (lane >> 3);
-                const int c0 = ch * KC + ku * 8;
-                // negated once, so that  T - (w1x cx + w1y cy)  is two FFMAs per channel
-                float nx[8], ny[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    nx[i] = -sw1x[c0 + i];
-                    ny[i] = -sw1y[c0 + i];
-                }
-#pragma unroll kAUnroll
-                for (int it = warp / kQuads; it < nb * 16; it += NW / kQuads) {
-                    const int sl = it >> 4, rg = it & 15;
-                    const int r = rg * 8 + (lane & 7);
-                    const int32_t pr = sidx[r * K + k0 + sl];
-                    const bool ok = pr >= 0;
-                    const float cx = scx[r], cy = scy[r];
-                    const float4 *trow = reinterpret_cast<const float4 *>(Tb + (size_t)(ok ? pr : 0) * C + c0);
-                    const float4 t0 = __ldg(trow), t1 = __ldg(trow + 1);
-                    const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(nx[i], cx, fmaf(ny[i], cy, t[i])), 0.0f);
-                    if (!__all_sync(0xffffffffu, ok)) {  // rare after compaction: rows without a k-th neighbour
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.0f;
-                    }
+                if (L::kChunks > 1) load_offset_weights(ch);
+                const float *Tc = Tb + ch * KC + ku * 8;
+                const float *neg = g_neg_row + ch * KC + ku * 8;
+                // one item = 8 rows x 32 channels per warp: lane (r8, u) turns 8 channels of one neighbour row into two
+                // 16-byte operand units (hi, lo).  Per item and lane: 2 LDS, 2 LDG.128, 8 FFMA2, 8 F2FP, 8 unpack, 4 FADD2,
+                // 2 STS.128 -- rows without a k-th neighbour read a row of -1e30, which the fused ReLU turns into zeros.
+                // The gathers of a whole batch of items are issued before the first one is consumed (L2 latency is paid
+                // once per batch, not once per item).
+                constexpr int kStep = NW / kQuads;   // row groups between two items of a warp
+                const int rg0 = warp / kQuads;
+                const uint32_t idx0 = sidx_addr + (uint32_t)(((par * K + k) * kTile + rg0 * 8 + r8) * 4);
+                const uint32_t ctr0 = sctr_addr + (uint32_t)((par * kTile + rg0 * 8 + r8) * 16);
+                const uint32_t dst0 = sA_addr + tc::unit_offset(r8, ku, kc_units) + (uint32_t)(rg0 * kc_units * 128);
+                auto gather = [&](uint32_t idx_addr, float4 &t0, float4 &t1) {
+                    const int32_t pr = (int32_t)tc::lds_u32(idx_addr);
+                    const float4 *trow = reinterpret_cast<const float4 *>(pr >= 0 ? Tc + (size_t)pr * C : neg);
+                    t0 = __ldg(trow);
+                    t1 = __ldg(trow + 1);
+                };
+                auto build = [&](const float4 &t0, const float4 &t1, uint32_t ctr_addr, uint32_t dst_addr) {
+                    const float4 ctr = tc::lds_f32x4(ctr_addr);
+                    const float2 cxx = make_float2(ctr.x, ctr.y), cyy = make_float2(ctr.z, ctr.w);
+                    float2 v[4];
+                    v[0] = tc::ffma2(nx[0], cxx, tc::ffma2(ny[0], cyy, make_float2(t0.x, t0.y)));
+                    v[1] = tc::ffma2(nx[1], cxx, tc::ffma2(ny[1], cyy, make_float2(t0.z, t0.w)));
+                    v[2] = tc::ffma2(nx[2], cxx, tc::ffma2(ny[2], cyy, make_float2(t1.x, t1.y)));
+                    v[3] = tc::ffma2(nx[3], cxx, tc::ffma2(ny[3], cyy, make_float2(t1.z, t1.w)));
                     uint4 hi, lo;
-                    tc::split_bf16x8(v, hi, lo, NS == 2);
-                    uint8_t *dst = sA + sl * L::kASlotBytes + tc::unit_offset(r, ku, kc_units);
-                    *reinterpret_cast<uint4 *>(dst) = hi;
-                    if (NS == 2) *reinterpret_cast<uint4 *>(dst + kTile * KC * 2) = lo;
+                    tc::relu_split_bf16x8(v, hi, lo, NS == 2);
+                    tc::sts_u32x4(dst_addr, hi);
+                    if (NS == 2) tc::sts_u32x4(dst_addr + kTile * KC * 2, lo);
+                };
+                if (16 % kStep == 0) {
+                    constexpr int kItems = 16 / kStep;
+                    constexpr int kBatch = kItems < kGatherBatch ? kItems : kGatherBatch;
+#pragma unroll
+                    for (int i0 = 0; i0 < kItems; i0 += kBatch) {
+                        float4 t0[kBatch], t1[kBatch];
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i) gather(idx0 + (i0 + i) * kStep * 32, t0[i], t1[i]);
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i)
+                            build(t0[i], t1[i], ctr0 + (i0 + i) * kStep * 128, dst0 + (i0 + i) * kStep * kc_units * 128);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int rg = rg0; rg < 16; rg += 2 * kStep) {   // pairs of items
+                        float4 t0[2], t1[2];
+                        const bool two = rg + kStep < 16;
+                        gather(idx0 + (rg - rg0) * 32, t0[0], t1[0]);
+                        if (two) gather(idx0 + (rg - rg0 + kStep) * 32, t0[1], t1[1]);
+                        build(t0[0], t1[0], ctr0 + (rg - rg0) * 128, dst0 + (rg - rg0) * kc_units * 128);
+                        if (two) build(t0[1], t1[1], ctr0 + (rg - rg0 + kStep) * 128, dst0 + (rg - rg0 + kStep) * kc_units * 128);
+                    }
                 }
+                if (ch == 0 && grp == 0) *ab_row = sidx_k[row] >= 0 ? 0x3F803F80u : 0u;   // bf16 (1, 1) or (0, 0)
                 tc::fence_proxy_async();
                 tc::fence_before_sync();
                 __syncthreads();
                 if (tid == 0) {
                     tc::fence_after_sync();
-                    for (int sl = 0; sl < nb; ++sl)
-                        issue_chunk<C, NS, KC>(sA_addr + sl * L::kASlotBytes, sW_addr, tmem_acc + sl * C, ch > 0);
+                    if (ch == 0)
+                        tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr, 128, 256), idesc, 0u);
+                    issue_chunk<C, NS, KC>(sA_addr, sW_addr, tmem_acc, true);
                     tc::commit(bar);
                 }
                 tc::mbar_wait(bar, phase);
                 phase ^= 1u;
                 tc::fence_after_sync();
             }
-            // ---- epilogue of the round: pooled (+)= sum over its slots of valid ? relu(acc + b2) : 0 ------------------
+            // ---- epilogue of the round: pooled (+)= relu(acc)   (bias and valid mask are already inside acc) -----------
             __syncwarp();
 #pragma unroll 1
             for (int cc = grp; cc < kChunksE; cc += G) {
-                float s[EW];
-                if (pooled_live) {
-                    tc::tmem_ld<EW>(tmem_pool + lane_off + cc * EW, s);
+                float z[EW], s[EW];
+                if (k > 0) {
+                    tc::tmem_ld16x2(tmem_acc + lane_off + cc * EW, tmem_pool + lane_off + cc * EW, z, s);
+#pragma unroll
+                    for (int i = 0; i < EW; i += 2) {
+                        const float2 a = tc::fadd2(make_float2(s[i], s[i + 1]), make_float2(fmaxf(z[i], 0.f), fmaxf(z[i + 1], 0.f)));
+                        s[i] = a.x;
+                        s[i + 1] = a.y;
+                    }
                 } else {
+                    tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
 #pragma unroll
-                    for (int i = 0; i < EW; ++i) s[i] = 0.0f;
-                }
-                for (int sl = 0; sl < nb; ++sl) {
-                    const bool valid = sidx[row * K + k0 + sl] >= 0;
-                    float z[EW];
-                    tc::tmem_ld<EW>(tmem_acc + sl * C + lane_off + cc * EW, z);
-#pragma unroll
-                    for (int i4 = 0; i4 < EW / 4; ++i4) {
-                        const float4 bb = *reinterpret_cast<const float4 *>(sb2 + cc * EW + i4 * 4);
-                        const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) z[i4 * 4 + i] = fmaxf(z[i4 * 4 + i] + bq[i], 0.0f);
-                    }
-                    if (__all_sync(0xffffffffu, valid)) {  // the common case after compaction: no mask needed
-#pragma unroll
-                        for (int i = 0; i < EW; ++i) s[i] += z[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < EW; ++i) s[i] += valid ? z[i] : 0.0f;
-                    }
+                    for (int i = 0; i < EW; ++i) s[i] = fmaxf(z[i], 0.f);
                 }
                 tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);
             }
-            pooled_live = true;
             tc::fence_before_sync();  // TMEM accesses above are ordered before the next MMA by the next barrier
         }
 
-        if (pooled_live) {
-            // ---- layer 3: acc = pooled * W3^T --------------------------------------------------------------------------
+        if (R > 0) {
+            // ---- layer 3: acc = n_valid * b3 + pooled * W3^T -----------------------------------------------------------
             for (int ch = 0; ch < L::kChunks; ++ch) {
                 if (!L::kResident) copy_chunk<NT>(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
                 __syncwarp();
@@ -405,22 +480,29 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     tc::tmem_ld<EW>(tmem_pool + lane_off + ch * KC + cc * EW, s);
 #pragma unroll
                     for (int q = 0; q < EW / 8; ++q) {
-                        float v[8];
+                        float2 v[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = s[q * 8 + i];
+                        for (int i = 0; i < 4; ++i) v[i] = make_float2(s[q * 8 + 2 * i], s[q * 8 + 2 * i + 1]);
                         uint4 hi, lo;
-                        tc::split_bf16x8(v, hi, lo, NS == 2);
+                        tc::relu_split_bf16x8(v, hi, lo, NS == 2);   // pooled >= 0: the ReLU is the identity here
                         const uint32_t off = tc::unit_offset(row, cc * (EW / 8) + q, kc_units);
                         *reinterpret_cast<uint4 *>(sA + off) = hi;
                         if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
                     }
+                }
+                if (ch == 0 && grp == 0) {
+                    const uint32_t nv16 = __float_as_uint((float)n_valid) >> 16;   // small integers are exact in bf16
+                    *ab_row = nv16 | (nv16 << 16);
                 }
                 tc::fence_proxy_async();
                 tc::fence_before_sync();
                 __syncthreads();
                 if (tid == 0) {
                     tc::fence_after_sync();
-                    issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : 0), tmem_acc, ch > 0);
+                    if (ch == 0)
+                        tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr + L::kWbBytes, 128, 256),
+                                     idesc, 0u);
+                    issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : 0), tmem_acc, true);
                     tc::commit(bar);
                 }
                 tc::mbar_wait(bar, phase);
@@ -428,34 +510,36 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                 tc::fence_after_sync();
             }
         }
-        // ---- final epilogue: out = bev + acc + n_valid * b3 (thread = cell: a warp touches 128 contiguous bytes) --
-        const float nv = (float)n_valid;
+        // ---- final epilogue: out = bev + acc (thread = cell: a warp touches 128 contiguous bytes per channel) ---------
         __syncwarp();
+        if (R > 0 || p.out != p.bev) {
 #pragma unroll 1
-        for (int cc = grp; cc < kChunksE; cc += G) {
-            float z[EW];
-            if (pooled_live) tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
-            if (in_range) {
-                const size_t base = ((size_t)b * C + cc * EW) * cells + cell;
-                float bv[EW];
+            for (int cc = grp; cc < kChunksE; cc += G) {
+                float z[EW];
+                if (R > 0) tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
+                if (in_range) {
+                    const float *src = p.bev + ((size_t)b * C + cc * EW) * cells + cell;
+                    float *dst = p.out + ((size_t)b * C + cc * EW) * cells + cell;
 #pragma unroll
-                for (int i = 0; i < EW; ++i) bv[i] = __ldg(p.bev + base + (size_t)i * cells);
+                    for (int h = 0; h < EW; h += 8) {   // 8 loads in flight, then 8 stores
+                        float bv[8];
 #pragma unroll
-                for (int i = 0; i < EW; ++i) {
-                    const float add = pooled_live ? z[i] + nv * sb3[cc * EW + i] : 0.0f;
-                    p.out[base + (size_t)i * cells] = bv[i] + add;
+                        for (int i = 0; i < 8; ++i) bv[i] = __ldcs(src + (size_t)(h + i) * cells);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) __stcs(dst + (size_t)(h + i) * cells, R > 0 ? bv[i] + z[h + i] : bv[i]);
+                    }
                 }
             }
         }
+        // no barrier here: the tile header state (indices, centres, round count) is double-buffered by tile parity, and
+        // every other shared / tensor-memory buffer is only rewritten behind the next tile's first barrier
         tc::fence_before_sync();
-        __syncthreads();  // sidx / A / TMEM are reused by the next tile
-        tc::fence_after_sync();
     }
 
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);
 }
-
 // ---------------------------------------------------------------------------------------------------------------
 // K-4a on tensor cores:  T[b, m, :] = feat[b, m, :] W1[:, :Ci]^T + W1[:, Ci:Ci+3] p_m + b1      (m < num_points[b])
 // Tile = 128 points.  W1's image part stays resident in shared memory; the rank-3 offset term and the bias are
@@ -699,20 +783,20 @@ int launch_tc(const TcParams &p, cudaStream_t st)
 {
     using L = TcLayout<C, NS>;
     constexpr int NT = kTile * TcShape<C>::G;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                L::kSmemBytes),
+    const int smem = L::smem_bytes(p.K);
+    static int attr_bytes = 0;
+    if (smem > attr_bytes) {
+        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                            "k_fusion_tc smem attribute"));
-        attr_set = true;
+        attr_bytes = smem;
     }
     // CTAs per SM: limited by shared memory, TMEM columns (512 per SM, never oversubscribed) and threads
-    const int by_smem = (227 * 1024) / (L::kSmemBytes + 1024);
-    const int by_tmem = 512 / L::kTmemCols;  // (SB + 1) * C columns per CTA, rounded up to a power of two
+    const int by_smem = (227 * 1024) / (smem + 1024);
+    const int by_tmem = 512 / L::kTmemCols;  // 2 * C columns per CTA, rounded up to a power of two
     const int by_threads = 2048 / NT;
     const int per_sm = std::max(1, std::min(std::min(by_smem, by_tmem), std::min(by_threads, 8)));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
-    k_fusion_tc<C, NS><<<(unsigned)grid, NT, L::kSmemBytes, st>>>(p);
+    k_fusion_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
 
@@ -737,8 +821,8 @@ int fusion_tc_pack(const float *d_W2, const float *d_W3, int32_t C, int32_t mode
 size_t fusion_tc_workspace_bytes(int32_t C, int32_t mode, int32_t B, int32_t H, int32_t W)
 {
     const int NS = mode == CF_MODE_FP32 ? 2 : 1;
-    // packed W2/W3 images | per-frame live-cell counts | per-frame live-cell lists
-    return tc_weight_bytes(C, NS) + 256 + (size_t)B * H * W * sizeof(int32_t);
+    // packed W2/W3 images | per-frame counts (with / without a neighbour) | per-frame cell lists
+    return tc_weight_bytes(C, NS) + 512 + (size_t)B * H * W * sizeof(int32_t);
 }
 
 int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H,
@@ -753,16 +837,16 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     const uint8_t *img2 = d_packed ? (const uint8_t *)d_packed : (const uint8_t *)d_workspace;
     const uint8_t *img3 = img2 + (size_t)NS * C * C * 2;
     int32_t *cell_count = (int32_t *)((uint8_t *)d_workspace + tc_weight_bytes(C, NS));
-    int32_t *cell_list = cell_count + 64;
+    int32_t *cell_list = cell_count + 128;
     CF_REQUIRE(B <= 64, CF_ERR_ARG, "cf_fusion_fwd: batch %d > 64 frames per call", B);
     const int64_t n_cells = (int64_t)H * W;
     // Compaction pays when there are many more tiles than SMs; on the small coarse scales it would only reduce the
-    // number of CTAs that have work, so those run every tile (empty tiles just copy bev -> out).
+    // number of CTAs that have work, so those run every tile (tiles without any neighbour just copy bev -> out).
     const bool compact = ceil_div64(n_cells, kTile) * B >= 4 * (int64_t)sm_count();
     if (compact) {
-        CF_TRY(cuda_status(cudaMemsetAsync(cell_count, 0, 256, st), "cf_fusion_fwd memset"));
-        k_cell_compact<<<dim3((unsigned)ceil_div64(n_cells, 256), (unsigned)B), 256, 0, st>>>(d_knn, K, n_cells, C, d_bev,
-                                                                                            d_out, cell_list, cell_count);
+        CF_TRY(cuda_status(cudaMemsetAsync(cell_count, 0, 512, st), "cf_fusion_fwd memset"));
+        k_cell_compact<<<dim3((unsigned)ceil_div64(n_cells, 256), (unsigned)B), 256, 0, st>>>(d_knn, K, n_cells, cell_list,
+                                                                                            cell_count);
         count_launches(1);
     }
     if (!d_packed) {
@@ -779,6 +863,7 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     p.tiles_total = p.tiles_per_frame * B;
     p.cell_list = compact ? cell_list : nullptr;
     p.cell_count = cell_count;
+    p.copy_dead = compact && d_out != d_bev;
     int rc = CF_ERR_UNSUPPORTED;
 #define CF_TC_CASE(c)                                                          \
     case c:                                                                    \

@@ -87,6 +87,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!done);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier among `nthreads` threads of the CTA (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------------------
 // one full warp; writes the base address to *dst (shared memory).  ncols: power of two in [32, 512]
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst, uint32_t ncols)
@@ -204,6 +214,111 @@ __device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4 &hi, uin
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+
+// ---- explicit shared-state-space accesses (32-bit addresses: no generic-pointer conversion in the inner loops) -----
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 process two fp32 lanes per issue slot) -----------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<unsigned long long &>(d))
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)),
+          "l"(reinterpret_cast<const unsigned long long &>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<unsigned long long &>(d))
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b)
+{
+    float2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<unsigned long long &>(d))
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+    return d;
+}
+
+// ReLU fused into the bf16 split of a NON-NEGATIVE-after-ReLU operand (activations):
+//   hi = bf16_rz(relu(v))              one F2FP.RELU.RZ per pair; truncation keeps hi <= v, so for v >= 0 the residual
+//   lo = bf16_rn(relu(v - float(hi)))  is >= 0, and for v < 0 (hi = 0) the residual v < 0 is clamped to 0 by the same
+//                                      .relu: no FMNMX, no select.  |relu(v) - hi - lo| < 2^-16 |v|.
+// a = element 0 (low half of the result), b = element 1 (high half).
+__device__ __forceinline__ uint32_t cvt_relu_rz_bf16x2(float a, float b)
+{
+    uint32_t d;
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt_relu_rn_bf16x2(float a, float b)
+{
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ void relu_split_bf16x8(const float2 (&v)[4], uint4 &hi, uint4 &lo, bool want_lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (want_lo) {
+            h[i] = cvt_relu_rz_bf16x2(v[i].x, v[i].y);
+            const float2 hf = make_float2(__uint_as_float(h[i] << 16), __uint_as_float(h[i] & 0xFFFF0000u));
+            const float2 r = fsub2(v[i], hf);
+            l[i] = cvt_relu_rn_bf16x2(r.x, r.y);
+        } else {
+            h[i] = cvt_relu_rn_bf16x2(v[i].x, v[i].y);
+            l[i] = 0;
+        }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// two 32-lane x 16-column TMEM loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a[i] = __uint_as_float(r[i]);
+        b[i] = __uint_as_float(r[16 + i]);
+    }
 }
 
 }  // namespace tc

@@ -65,17 +65,16 @@ __host__ __device__ constexpr int kc_for(int C, int NS)
     return C <= 128 ? C : 64;
 }
 
-#ifndef CF_GATHER_BATCH
-#define CF_GATHER_BATCH 4
-#endif
-constexpr int kGatherBatch = CF_GATHER_BATCH;  // neighbour-row gathers in flight per lane
 // launch shape of the two small-C instantiations (measured on B200, BASELINE configs[1]: several small CTAs per SM --
 // more independent tiles in flight -- beat fewer barrier rounds per tile; see profiles/README.md)
+#ifndef CF_PIPE
+#define CF_PIPE 1
+#endif
 #ifndef CF_G32
 #define CF_G32 1
 #define CF_G64 2
-#define CF_MB32 5
-#define CF_MB64 3
+#define CF_MB32 4
+#define CF_MB64 2
 #endif
 
 __host__ __device__ constexpr int tmem_cols_for(int cols)
@@ -84,6 +83,10 @@ __host__ __device__ constexpr int tmem_cols_for(int cols)
 }
 
 constexpr int kEW = 16;  // TMEM columns per epilogue step
+#ifndef CF_COPY_BATCH
+#define CF_COPY_BATCH 16
+#endif
+constexpr int kCopyBatch = CF_COPY_BATCH;  // channels per copy unit and thread loaded before the first store
 
 // the "row" a cell without a k-th neighbour gathers: relu(-1e30 - e) = 0, so the operand build needs no select
 #define CF_NEG8 -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f
@@ -107,7 +110,8 @@ struct TcLayout {
     static constexpr int kOffWb = kOffAb + kAbBytes;                // bias B operands: 2 layers x (C rows x 16 bf16)
     static constexpr int kWbBytes = C * 32;
     static constexpr int kOffCtr = kOffWb + 2 * kWbBytes;           // float4 (cx,cx,cy,cy) [2][128]
-    static constexpr int kOffW1 = kOffCtr + 2 * kTile * 16;         // float w1x[C], w1y[C]
+    static constexpr int kOffCell = kOffCtr + 2 * kTile * 16;       // int32 cell of each row [2][128]
+    static constexpr int kOffW1 = kOffCell + 2 * kTile * 4;         // float w1x[C], w1y[C]
     static constexpr int kOffBar = kOffW1 + 2 * C * 4;              // mbarrier (8 B), tmem ptr (4 B), pad, int wmax[2][4]
     static constexpr int kOffIdx = kOffBar + 48;                    // int32 [2][K][128] (K known at launch)
     static __host__ __device__ constexpr int smem_bytes(int K) { return kOffIdx + 2 * K * kTile * 4; }
@@ -232,15 +236,15 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     constexpr int KC = L::KC;
     constexpr int kc_units = KC / 8;
     constexpr int kChunksE = C / EW;  // epilogue chunks over all C columns
-    static_assert(C % G == 0 && (C / G) % 8 == 0, "column split between the thread groups");
+    static_assert(C % G == 0 && (C / G) % 32 == 0, "column split between the thread groups");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sW = smem;
     uint8_t *sA = smem + L::kOffA;
     uint8_t *sAb = smem + L::kOffAb;
     uint8_t *sWb = smem + L::kOffWb;
     float4 *sctr = reinterpret_cast<float4 *>(smem + L::kOffCtr);
-    float *sw1x = reinterpret_cast<float *>(smem + L::kOffW1);
-    float *sw1y = sw1x + C;
+    int32_t *scell = reinterpret_cast<int32_t *>(smem + L::kOffCell);
+    float *swn = reinterpret_cast<float *>(smem + L::kOffW1);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8);
     int32_t *swmax = reinterpret_cast<int32_t *>(smem + L::kOffBar + 16);   // [2][4]
@@ -259,9 +263,10 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(tmem_slot, L::kTmemCols);
+    // negated offset weights, per block of 8 channels: -w1x[8] | -w1y[8]  (what one lane of the operand build needs)
     for (int c = tid; c < C; c += NT) {
-        sw1x[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci);
-        sw1y[c] = __ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci + 1);
+        swn[(c >> 3) * 16 + (c & 7)] = -__ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci);
+        swn[(c >> 3) * 16 + 8 + (c & 7)] = -__ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci + 1);
     }
     // bias operands.  A side (rewritten per round): row r, k-columns 0 and 1 = the row's flag, the other 14 stay 0.
     // B side: row n = (hi(b[n]), lo(b[n]), 0 ...), so flag * (hi + lo) lands in the accumulator with one K=16 step.
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
     const uint32_t sAb_addr = tc::smem_u32(sAb), sWb_addr = tc::smem_u32(sWb);
     const uint32_t sidx_addr = tc::smem_u32(sidx), sctr_addr = tc::smem_u32(sctr);
-    uint32_t *ab_row = reinterpret_cast<uint32_t *>(sAb + tc::unit_offset(row, 0, 2));
+    const uint32_t ab_row = sAb_addr + tc::unit_offset(row, 0, 2);
     constexpr uint32_t idesc = tc::make_idesc_bf16(kTile, C);
     uint32_t phase = 0, iter = 0;
 
@@ -301,245 +306,348 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     // the same 32 channels of a chunk and its negated offset weights stay in registers.
     constexpr int kQuads = kc_units / 4;
     static_assert(NW % kQuads == 0, "warps per CTA must be a multiple of the unit quads per row");
+    constexpr int kStep = NW / kQuads;   // row groups between two items of a warp
+    constexpr bool kEven = 16 % kStep == 0;
+    constexpr int kItems = kEven ? 16 / kStep : 1;
     const int ku = (warp % kQuads) * 4 + (lane >> 3);
     const int r8 = lane & 7;
-    float2 nx[4], ny[4];   // -(w1x, w1y) of this lane's 8 channels:  T - (w1x cx + w1y cy) = two FFMA2 per channel pair
+    const int rg0 = warp / kQuads;
+    // -(w1x, w1y) of this lane's 8 channels:  T - (w1x cx + w1y cy) = two FFMA2 per channel pair.  Reloaded from shared
+    // memory at the start of every round's build (4 LDS.128) rather than held across the whole tile.
+    float2 nx[4], ny[4];
+    const uint32_t swn_addr = tc::smem_u32(swn);
     auto load_offset_weights = [&](int ch) {
-        const int c0 = ch * KC + ku * 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            nx[i] = make_float2(-sw1x[c0 + 2 * i], -sw1x[c0 + 2 * i + 1]);
-            ny[i] = make_float2(-sw1y[c0 + 2 * i], -sw1y[c0 + 2 * i + 1]);
+        const uint32_t a = swn_addr + (uint32_t)((ch * kc_units + ku) * 64);
+        const float4 x0 = tc::lds_f32x4(a), x1 = tc::lds_f32x4(a + 16), y0 = tc::lds_f32x4(a + 32), y1 = tc::lds_f32x4(a + 48);
+        nx[0] = make_float2(x0.x, x0.y); nx[1] = make_float2(x0.z, x0.w); nx[2] = make_float2(x1.x, x1.y); nx[3] = make_float2(x1.z, x1.w);
+        ny[0] = make_float2(y0.x, y0.y); ny[1] = make_float2(y0.z, y0.w); ny[2] = make_float2(y1.x, y1.y); ny[3] = make_float2(y1.z, y1.w);
+    };
+
+    // ---- tile sequencing (uniform across the CTA) ------------------------------------------------------------------
+    // Tile t covers entries [e0, e0 + 128) of frame b's lists: of the cells WITH a neighbour (an MLP tile) and, from the
+    // other end, of the cells WITHOUT one (a copy unit).  The CTA walks both sequences with two cursors and interleaves
+    // them, so the memory-bound copies overlap the MLP tiles of the CTAs that share the SM.
+    // Positions in the tile sequence are (frame b, tile q within the frame); this CTA visits every gridDim.x-th tile.
+    const int32_t tpf = (int32_t)p.tiles_per_frame;
+    auto n_live_of = [&](int b) -> int32_t { return p.cell_list ? __ldg(p.cell_count + b) : (int32_t)cells; };
+    auto advance = [&](int32_t &b, int32_t &q, int32_t step) {
+        q += step;
+        while (q >= tpf) {
+            q -= tpf;
+            ++b;
         }
     };
-    if (L::kChunks == 1) load_offset_weights(0);
-
-    for (int64_t tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-        const int b = (int)(tile / p.tiles_per_frame);
-        const int64_t e0 = (tile - (int64_t)b * p.tiles_per_frame) * kTile;
-        const int32_t n_live = p.cell_list ? __ldg(p.cell_count + b) : (int32_t)cells;  // no list: every cell, in order
-        // ---- cells without a neighbour (back of the list): out = bev ---------------------------------------------------
-        if (p.copy_dead) {
-            const int64_t j = e0 + row;
-            if (j < cells - n_live) {
-                const int32_t dc = __ldg(p.cell_list + (size_t)b * cells + (cells - 1 - j));
-                constexpr int CG = C / G;
-                const size_t o = ((size_t)b * C + grp * CG) * cells + dc;
-#pragma unroll 1
-                for (int c = 0; c < CG; c += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __ldcs(p.bev + o + (size_t)(c + i) * cells);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) __stcs(p.out + o + (size_t)(c + i) * cells, v[i]);
-                }
-            }
-        }
-        if (e0 >= n_live) continue;  // uniform
-        // ---- tile header: cell, centre, neighbour indices (slot-major in shared memory), rounds of the tile ------------
-        const int par = iter & 1;
-        ++iter;
-        const bool in_range = e0 + row < n_live;
-        const int32_t cell = !in_range ? 0 : p.cell_list ? __ldg(p.cell_list + (size_t)b * cells + e0 + row) : (int32_t)(e0 + row);
-        int32_t *sidx_t = sidx + par * K * kTile;
-        int n_valid = 0;
-        {
+    auto seek_live = [&](int32_t &b, int32_t &q) {   // forward (inclusive) to the next tile that has rows; b == B: none
+        while (b < p.B && q * kTile >= n_live_of(b)) advance(b, q, (int32_t)gridDim.x);
+    };
+    // Tile header, prefetched one tile ahead by the 128 threads of group 0 (thread = row).
+    //   stage 1: the row's cell (-1: the list ends before this row)
+    //   stage 2: its K neighbour indices straight into shared memory (cp.async, slot-major), centre and cell
+    auto header_cell = [&](int32_t b, int32_t q) -> int32_t {
+        const int32_t e = q * kTile + row;
+        if (e >= n_live_of(b)) return -1;
+        return p.cell_list ? __ldg(p.cell_list + (size_t)b * cells + e) : e;
+    };
+    auto header_fill = [&](int32_t b, int32_t cell, int par) {
+        const uint32_t dst = sidx_addr + (uint32_t)((par * K * kTile + row) * 4);
+        float cx = 0.f, cy = 0.f;
+        if (cell >= 0) {
             const int32_t *kr = p.knn + ((size_t)b * cells + cell) * K;
-            for (int k = 0; k < K; ++k) {
-                const int32_t v = in_range ? __ldg(kr + k) : -1;
-                n_valid += v >= 0;
-                if (grp == 0) sidx_t[k * kTile + row] = v;
-            }
+            for (int k = 0; k < K; ++k) tc::cp_async4(dst + k * kTile * 4, kr + k);
+            const int32_t i = (int32_t)((uint32_t)cell / (uint32_t)p.W), j = cell - i * p.W;
+            cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
+            cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
+        } else {
+            for (int k = 0; k < K; ++k) tc::sts_u32(dst + k * kTile * 4, 0xFFFFFFFFu);
         }
-        if (grp == 0) {
-            float cx = 0.f, cy = 0.f;
-            if (in_range) {
-                const int32_t i = cell / p.W, j = cell - i * p.W;
-                cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
-                cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
-            }
-            sctr[par * kTile + row] = make_float4(cx, cx, cy, cy);
-            const int wm = __reduce_max_sync(0xffffffffu, n_valid);
-            if (lane == 0) swmax[par * 4 + warp] = wm;
-        }
-        __syncthreads();
-        // slots are sorted (empty ones form a suffix): the tile needs as many rounds as its best-connected cell
-        int R;
-        {
-            const int4 wm = *reinterpret_cast<const int4 *>(swmax + par * 4);
-            R = max(max(wm.x, wm.y), max(wm.z, wm.w));
-        }
-        const float4 *sctr_t = sctr + par * kTile;
-        const float *Tb = p.T + (size_t)b * p.N * C;
+        tc::cp_async_commit();
+        sctr[par * kTile + row] = make_float4(cx, cx, cy, cy);
+        scell[par * kTile + row] = cell;
+    };
 
-        for (int k = 0; k < R; ++k) {
-            const int32_t *sidx_k = sidx_t + k * kTile;
-            for (int ch = 0; ch < L::kChunks; ++ch) {
-                if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
-                if (L::kChunks > 1) load_offset_weights(ch);
-                const float *Tc = Tb + ch * KC + ku * 8;
-                const float *neg = g_neg_row + ch * KC + ku * 8;
-                // one item = 8 rows x 32 channels per warp: lane (r8, u) turns 8 channels of one neighbour row into two
-                // 16-byte operand units (hi, lo).  Per item and lane: 2 LDS, 2 LDG.128, 8 FFMA2, 8 F2FP, 8 unpack, 4 FADD2,
-                // 2 STS.128 -- rows without a k-th neighbour read a row of -1e30, which the fused ReLU turns into zeros.
-                // The gathers of a whole batch of items are issued before the first one is consumed (L2 latency is paid
-                // once per batch, not once per item).
-                constexpr int kStep = NW / kQuads;   // row groups between two items of a warp
-                const int rg0 = warp / kQuads;
-                const uint32_t idx0 = sidx_addr + (uint32_t)(((par * K + k) * kTile + rg0 * 8 + r8) * 4);
-                const uint32_t ctr0 = sctr_addr + (uint32_t)((par * kTile + rg0 * 8 + r8) * 16);
-                const uint32_t dst0 = sA_addr + tc::unit_offset(r8, ku, kc_units) + (uint32_t)(rg0 * kc_units * 128);
-                auto gather = [&](uint32_t idx_addr, float4 &t0, float4 &t1) {
-                    const int32_t pr = (int32_t)tc::lds_u32(idx_addr);
-                    const float4 *trow = reinterpret_cast<const float4 *>(pr >= 0 ? Tc + (size_t)pr * C : neg);
-                    t0 = __ldg(trow);
-                    t1 = __ldg(trow + 1);
-                };
-                auto build = [&](const float4 &t0, const float4 &t1, uint32_t ctr_addr, uint32_t dst_addr) {
-                    const float4 ctr = tc::lds_f32x4(ctr_addr);
-                    const float2 cxx = make_float2(ctr.x, ctr.y), cyy = make_float2(ctr.z, ctr.w);
-                    float2 v[4];
-                    v[0] = tc::ffma2(nx[0], cxx, tc::ffma2(ny[0], cyy, make_float2(t0.x, t0.y)));
-                    v[1] = tc::ffma2(nx[1], cxx, tc::ffma2(ny[1], cyy, make_float2(t0.z, t0.w)));
-                    v[2] = tc::ffma2(nx[2], cxx, tc::ffma2(ny[2], cyy, make_float2(t1.x, t1.y)));
-                    v[3] = tc::ffma2(nx[3], cxx, tc::ffma2(ny[3], cyy, make_float2(t1.z, t1.w)));
-                    uint4 hi, lo;
-                    tc::relu_split_bf16x8(v, hi, lo, NS == 2);
-                    tc::sts_u32x4(dst_addr, hi);
-                    if (NS == 2) tc::sts_u32x4(dst_addr + kTile * KC * 2, lo);
-                };
-                if (16 % kStep == 0) {
-                    constexpr int kItems = 16 / kStep;
-                    constexpr int kBatch = kItems < kGatherBatch ? kItems : kGatherBatch;
+    // ---- operand build ---------------------------------------------------------------------------------------------
+    // one item = 8 rows x 32 channels per warp: lane (r8, u) turns 8 channels of one neighbour row into two 16-byte
+    // operand units (hi, lo).  Per item and lane: 2 LDS, 2 LDG.128, 8 FFMA2, 8 F2FP, 8 unpack, 4 FADD2, 2 STS.128 --
+    // rows without a k-th neighbour read a row of -1e30, which the fused ReLU turns into zeros.
+    auto gather = [&](const float *Tc, const float *neg, uint32_t idx_addr, float *t) {   // t[8]
+        const int32_t pr = (int32_t)tc::lds_u32(idx_addr);
+        const float4 *trow = reinterpret_cast<const float4 *>(pr >= 0 ? Tc + (size_t)pr * C : neg);
+        const float4 a = __ldg(trow), c = __ldg(trow + 1);
+        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = c.x; t[5] = c.y; t[6] = c.z; t[7] = c.w;
+    };
+    auto build = [&](const float *t, const float4 &ctr, uint32_t dst_addr) {
+        const float2 cxx = make_float2(ctr.x, ctr.y), cyy = make_float2(ctr.z, ctr.w);
+        float2 v[4];
 #pragma unroll
-                    for (int i0 = 0; i0 < kItems; i0 += kBatch) {
-                        float4 t0[kBatch], t1[kBatch];
+        for (int i = 0; i < 4; ++i) v[i] = tc::ffma2(nx[i], cxx, tc::ffma2(ny[i], cyy, make_float2(t[2 * i], t[2 * i + 1])));
+        uint4 hi, lo;
+        tc::relu_split_bf16x8(v, hi, lo, NS == 2);
+        tc::sts_u32x4(dst_addr, hi);
+        if (NS == 2) tc::sts_u32x4(dst_addr + kTile * KC * 2, lo);
+    };
+
+    int32_t cb = 0, cq = 0, db = 0, dq = 0;   // cursors: MLP tiles (cb, cq), copy units (db, dq)
+    advance(cb, cq, (int32_t)blockIdx.x);
+    seek_live(cb, cq);
+    if (p.copy_dead) advance(db, dq, (int32_t)blockIdx.x); else db = p.B;
+    if (cb < p.B && grp == 0) header_fill(cb, header_cell(cb, cq), 0);
+
+    while (cb < p.B || db < p.B) {
+        if (cb < p.B) {
+            const int par = iter & 1;
+            ++iter;
+            const int b = cb;
+            int32_t nb = cb, nq = cq;
+            advance(nb, nq, (int32_t)gridDim.x);
+            seek_live(nb, nq);
+            const bool has_next = nb < p.B;
+            // ---- header of this tile (prefetched): rounds = neighbour count of its best-connected cell -----------------
+            int n_valid = 0;
+            if (grp == 0) {
+                tc::cp_async_wait_all();
+                for (int k = 0; k < K; ++k) n_valid += (int32_t)tc::lds_u32(sidx_addr + (uint32_t)(((par * K + k) * kTile + row) * 4)) >= 0;
+                const int wm = __reduce_max_sync(0xffffffffu, n_valid);
+                if (lane == 0) swmax[par * 4 + warp] = wm;
+            }
+            __syncthreads();
+            int R;
+            {
+                const int4 wm = *reinterpret_cast<const int4 *>(swmax + par * 4);
+                R = max(max(wm.x, wm.y), max(wm.z, wm.w));
+            }
+            const int32_t cell = scell[par * kTile + row];
+            const bool in_range = cell >= 0;
+            int32_t ncell = -1;   // stage 1 of the next tile's header: in flight during round 0
+            if (grp == 0 && has_next) ncell = header_cell(nb, nq);
+            if (R == 0 && grp == 0 && has_next) header_fill(nb, ncell, par ^ 1);
+
+            const float *Tb = p.T + (size_t)b * p.N * C;
+            const uint32_t idx0 = sidx_addr + (uint32_t)((par * K * kTile + rg0 * 8 + r8) * 4);
+            const uint32_t ctr0 = sctr_addr + (uint32_t)((par * kTile + rg0 * 8 + r8) * 16);
+            const uint32_t dst0 = sA_addr + tc::unit_offset(r8, ku, kc_units) + (uint32_t)(rg0 * kc_units * 128);
+            const float *src_bev = p.bev + (size_t)b * C * cells + cell;
+            // Pipelined shapes (both layers resident, 4 items per warp and round): tv holds the gathered neighbour rows
+            // of the NEXT round while this round's MMA and epilogue run; in the last round the same 32 registers take the
+            // bev values of this thread's first two output chunks instead.
+            constexpr bool kPipe = CF_PIPE && kEven && L::kChunks == 1 && kItems == 4;
+            constexpr int kPre = kPipe ? 2 : 0;   // output chunks whose bev values are prefetched
+            float tv[32];
+            auto prefetch_bev = [&]() {
+                if (kPipe && in_range) {
 #pragma unroll
-                        for (int i = 0; i < kBatch; ++i) gather(idx0 + (i0 + i) * kStep * 32, t0[i], t1[i]);
+                    for (int j = 0; j < 2; ++j) {
+                        if (grp + j * G < kChunksE) {
 #pragma unroll
-                        for (int i = 0; i < kBatch; ++i)
-                            build(t0[i], t1[i], ctr0 + (i0 + i) * kStep * 128, dst0 + (i0 + i) * kStep * kc_units * 128);
-                    }
-                } else {
-#pragma unroll 1
-                    for (int rg = rg0; rg < 16; rg += 2 * kStep) {   // pairs of items
-                        float4 t0[2], t1[2];
-                        const bool two = rg + kStep < 16;
-                        gather(idx0 + (rg - rg0) * 32, t0[0], t1[0]);
-                        if (two) gather(idx0 + (rg - rg0 + kStep) * 32, t0[1], t1[1]);
-                        build(t0[0], t1[0], ctr0 + (rg - rg0) * 128, dst0 + (rg - rg0) * kc_units * 128);
-                        if (two) build(t0[1], t1[1], ctr0 + (rg - rg0 + kStep) * 128, dst0 + (rg - rg0 + kStep) * kc_units * 128);
+                            for (int i = 0; i < EW; ++i) tv[j * EW + i] = __ldcs(src_bev + (size_t)((grp + j * G) * EW + i) * cells);
+                        }
                     }
                 }
-                if (ch == 0 && grp == 0) *ab_row = sidx_k[row] >= 0 ? 0x3F803F80u : 0u;   // bf16 (1, 1) or (0, 0)
-                tc::fence_proxy_async();
-                tc::fence_before_sync();
-                __syncthreads();
-                if (tid == 0) {
+            };
+            if (kPipe && R > 0) {
+                const float *Tc = Tb + ku * 8, *neg = g_neg_row + ku * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gather(Tc, neg, idx0 + i * kStep * 32, tv + 8 * i);
+            }
+            if (R == 0) prefetch_bev();
+
+            for (int k = 0; k < R; ++k) {
+                const uint32_t idxk = idx0 + (uint32_t)(k * kTile * 4);
+                for (int ch = 0; ch < L::kChunks; ++ch) {
+                    if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                    if (kPipe) {
+                        load_offset_weights(0);
+                        // rows were gathered while the previous round's MMA and epilogue ran
+                        // (the centre of item i+1 is loaded before item i is stored: the shared-memory latency hides
+                        // behind the arithmetic of the previous item)
+                        float4 ctr = tc::lds_f32x4(ctr0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 ctr_next = ctr;
+                            if (i < 3) ctr_next = tc::lds_f32x4(ctr0 + (i + 1) * kStep * 128);
+                            build(tv + 8 * i, ctr, dst0 + i * kStep * kc_units * 128);
+                            ctr = ctr_next;
+                        }
+                    } else {
+                        load_offset_weights(ch);
+                        const float *Tc = Tb + ch * KC + ku * 8, *neg = g_neg_row + ch * KC + ku * 8;
+#pragma unroll 1
+                        for (int rg = rg0; rg < 16; rg += 2 * kStep) {   // pairs of items: both gathers in flight
+                            float ta[8], tb[8];
+                            const bool two = rg + kStep < 16;
+                            gather(Tc, neg, idxk + (rg - rg0) * 32, ta);
+                            if (two) gather(Tc, neg, idxk + (rg - rg0 + kStep) * 32, tb);
+                            const float4 ca = tc::lds_f32x4(ctr0 + (rg - rg0) * 128);
+                            const float4 cb = tc::lds_f32x4(ctr0 + (two ? rg - rg0 + kStep : rg - rg0) * 128);
+                            build(ta, ca, dst0 + (rg - rg0) * kc_units * 128);
+                            if (two) build(tb, cb, dst0 + (rg - rg0 + kStep) * kc_units * 128);
+                        }
+                    }
+                    if (ch == 0 && grp == 0)   // bias flag of the row: bf16 (1, 1) or (0, 0)
+                        tc::sts_u32(ab_row, (int32_t)tc::lds_u32(sidx_addr + (uint32_t)(((par * K + k) * kTile + row) * 4)) >= 0 ? 0x3F803F80u : 0u);
+                    tc::fence_proxy_async();
+                    tc::fence_before_sync();
+                    __syncthreads();
+                    if (tid == 0) {
+                        tc::fence_after_sync();
+                        if (ch == 0)
+                            tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr, 128, 256), idesc, 0u);
+                        issue_chunk<C, NS, KC>(sA_addr, sW_addr, tmem_acc, true);
+                        tc::commit(bar);
+                    }
+                    if (ch == L::kChunks - 1) {
+                        // work that overlaps this round's MMA and epilogue: the next tile's header, then the next round's
+                        // gathers (or, in the last round, the bev values of the final epilogue)
+                        if (k == 0 && grp == 0 && has_next) header_fill(nb, ncell, par ^ 1);
+                        if (k + 1 < R) {
+                            if (kPipe) {
+                                const float *Tc = Tb + ku * 8, *neg = g_neg_row + ku * 8;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) gather(Tc, neg, idxk + kTile * 4 + i * kStep * 32, tv + 8 * i);
+                            }
+                        } else {
+                            prefetch_bev();
+                        }
+                    }
+                    tc::mbar_wait(bar, phase);
+                    phase ^= 1u;
                     tc::fence_after_sync();
-                    if (ch == 0)
-                        tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr, 128, 256), idesc, 0u);
-                    issue_chunk<C, NS, KC>(sA_addr, sW_addr, tmem_acc, true);
-                    tc::commit(bar);
                 }
-                tc::mbar_wait(bar, phase);
-                phase ^= 1u;
-                tc::fence_after_sync();
-            }
-            // ---- epilogue of the round: pooled (+)= relu(acc)   (bias and valid mask are already inside acc) -----------
-            __syncwarp();
-#pragma unroll 1
-            for (int cc = grp; cc < kChunksE; cc += G) {
-                float z[EW], s[EW];
-                if (k > 0) {
-                    tc::tmem_ld16x2(tmem_acc + lane_off + cc * EW, tmem_pool + lane_off + cc * EW, z, s);
-#pragma unroll
-                    for (int i = 0; i < EW; i += 2) {
-                        const float2 a = tc::fadd2(make_float2(s[i], s[i + 1]), make_float2(fmaxf(z[i], 0.f), fmaxf(z[i + 1], 0.f)));
-                        s[i] = a.x;
-                        s[i + 1] = a.y;
-                    }
-                } else {
-                    tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
-#pragma unroll
-                    for (int i = 0; i < EW; ++i) s[i] = fmaxf(z[i], 0.f);
-                }
-                tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);
-            }
-            tc::fence_before_sync();  // TMEM accesses above are ordered before the next MMA by the next barrier
-        }
-
-        if (R > 0) {
-            // ---- layer 3: acc = n_valid * b3 + pooled * W3^T -----------------------------------------------------------
-            for (int ch = 0; ch < L::kChunks; ++ch) {
-                if (!L::kResident) copy_chunk<NT>(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                // ---- epilogue of the round: pooled (+)= relu(acc)   (bias and valid mask are already inside acc) -----------
                 __syncwarp();
 #pragma unroll 1
-                for (int cc = grp; cc < KC / EW; cc += G) {
-                    float s[EW];
-                    tc::tmem_ld<EW>(tmem_pool + lane_off + ch * KC + cc * EW, s);
+                for (int cc = grp; cc < kChunksE; cc += G) {
+                    float z[EW], s[EW];
+                    if (k > 0) {
+                        tc::tmem_ld16x2(tmem_acc + lane_off + cc * EW, tmem_pool + lane_off + cc * EW, z, s);
 #pragma unroll
-                    for (int q = 0; q < EW / 8; ++q) {
-                        float2 v[4];
+                        for (int i = 0; i < EW; i += 2) {
+                            const float2 a = tc::fadd2(make_float2(s[i], s[i + 1]), make_float2(fmaxf(z[i], 0.f), fmaxf(z[i + 1], 0.f)));
+                            s[i] = a.x;
+                            s[i + 1] = a.y;
+                        }
+                    } else {
+                        tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = make_float2(s[q * 8 + 2 * i], s[q * 8 + 2 * i + 1]);
-                        uint4 hi, lo;
-                        tc::relu_split_bf16x8(v, hi, lo, NS == 2);   // pooled >= 0: the ReLU is the identity here
-                        const uint32_t off = tc::unit_offset(row, cc * (EW / 8) + q, kc_units);
-                        *reinterpret_cast<uint4 *>(sA + off) = hi;
-                        if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * KC * 2 + off) = lo;
+                        for (int i = 0; i < EW; ++i) s[i] = fmaxf(z[i], 0.f);
                     }
+                    tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);
                 }
-                if (ch == 0 && grp == 0) {
-                    const uint32_t nv16 = __float_as_uint((float)n_valid) >> 16;   // small integers are exact in bf16
-                    *ab_row = nv16 | (nv16 << 16);
-                }
-                tc::fence_proxy_async();
-                tc::fence_before_sync();
-                __syncthreads();
-                if (tid == 0) {
-                    tc::fence_after_sync();
-                    if (ch == 0)
-                        tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr + L::kWbBytes, 128, 256),
-                                     idesc, 0u);
-                    issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : 0), tmem_acc, true);
-                    tc::commit(bar);
-                }
-                tc::mbar_wait(bar, phase);
-                phase ^= 1u;
-                tc::fence_after_sync();
+                tc::fence_before_sync();  // TMEM accesses above are ordered before the next MMA by the next barrier
             }
-        }
-        // ---- final epilogue: out = bev + acc (thread = cell: a warp touches 128 contiguous bytes per channel) ---------
-        __syncwarp();
-        if (R > 0 || p.out != p.bev) {
+
+            if (R > 0) {
+                // ---- layer 3: acc = n_valid * b3 + pooled * W3^T -----------------------------------------------------------
+                for (int ch = 0; ch < L::kChunks; ++ch) {
+                    if (!L::kResident) copy_chunk<NT>(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
+                    __syncwarp();
 #pragma unroll 1
-            for (int cc = grp; cc < kChunksE; cc += G) {
-                float z[EW];
-                if (R > 0) tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
-                if (in_range) {
-                    const float *src = p.bev + ((size_t)b * C + cc * EW) * cells + cell;
-                    float *dst = p.out + ((size_t)b * C + cc * EW) * cells + cell;
+                    for (int cc = grp; cc < KC / EW; cc += G) {
+                        float s[EW];
+                        tc::tmem_ld<EW>(tmem_pool + lane_off + ch * KC + cc * EW, s);
 #pragma unroll
-                    for (int h = 0; h < EW; h += 8) {   // 8 loads in flight, then 8 stores
-                        float bv[8];
+                        for (int q = 0; q < EW / 8; ++q) {
+                            float2 v[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) bv[i] = __ldcs(src + (size_t)(h + i) * cells);
+                            for (int i = 0; i < 4; ++i) v[i] = make_float2(s[q * 8 + 2 * i], s[q * 8 + 2 * i + 1]);
+                            uint4 hi, lo;
+                            tc::relu_split_bf16x8(v, hi, lo, NS == 2);   // pooled >= 0: the ReLU is the identity here
+                            const uint32_t off = sA_addr + tc::unit_offset(row, cc * (EW / 8) + q, kc_units);
+                            tc::sts_u32x4(off, hi);
+                            if (NS == 2) tc::sts_u32x4(off + kTile * KC * 2, lo);
+                        }
+                    }
+                    if (ch == 0 && grp == 0) {
+                        const uint32_t nv16 = __float_as_uint((float)n_valid) >> 16;   // small integers are exact in bf16
+                        tc::sts_u32(ab_row, nv16 | (nv16 << 16));
+                    }
+                    tc::fence_proxy_async();
+                    tc::fence_before_sync();
+                    __syncthreads();
+                    if (tid == 0) {
+                        tc::fence_after_sync();
+                        if (ch == 0)
+                            tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr + L::kWbBytes, 128, 256),
+                                         idesc, 0u);
+                        issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : 0), tmem_acc, true);
+                        tc::commit(bar);
+                    }
+                    tc::mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    tc::fence_after_sync();
+                }
+            }
+            // ---- final epilogue: out = bev + acc (thread = cell: a warp touches 128 contiguous bytes per channel) ---------
+            __syncwarp();
+            if (R > 0 || p.out != p.bev) {
+                float *dst_out = p.out + (size_t)b * C * cells + cell;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) __stcs(dst + (size_t)(h + i) * cells, R > 0 ? bv[i] + z[h + i] : bv[i]);
+                for (int j = 0; j < (kChunksE + G - 1) / G; ++j) {
+                    const int cc = grp + j * G;
+                    if (cc < kChunksE) {
+                        float z[EW];
+                        if (R > 0) tc::tmem_ld<EW>(tmem_acc + lane_off + cc * EW, z);
+                        if (in_range) {
+                            if (j < kPre) {
+#pragma unroll
+                                for (int i = 0; i < EW; ++i)
+                                    __stcs(dst_out + (size_t)(cc * EW + i) * cells, R > 0 ? tv[(j & 1) * EW + i] + z[i] : tv[(j & 1) * EW + i]);
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < EW; h += 8) {   // 8 loads in flight, then 8 stores
+                                    float bv[8];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) bv[i] = __ldcs(src_bev + (size_t)(cc * EW + h + i) * cells);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        __stcs(dst_out + (size_t)(cc * EW + h + i) * cells, R > 0 ? bv[i] + z[h + i] : bv[i]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // no barrier here: the tile header state (indices, centres, cells, round count) is double-buffered by tile
+            // parity, and every other shared / tensor-memory buffer is only rewritten behind the next tile's first barrier
+            tc::fence_before_sync();
+            cb = nb;
+            cq = nq;
+        }
+        // ---- copy units: cells without a neighbour (back of the list): out = bev ----------------------------------------
+        // (thread = cell, the G thread groups split the channels; two units are interleaved after every MLP tile)
+        for (int d = 0; d < 2 && db < p.B; advance(db, dq, (int32_t)gridDim.x)) {
+            const int32_t n_dead = (int32_t)cells - n_live_of(db);
+            if (dq * kTile >= n_dead) continue;   // uniform: nothing left in this frame's list for this tile slot
+            ++d;
+            const int32_t j = dq * kTile + row;
+            if (j < n_dead) {
+                const int32_t dc = __ldg(p.cell_list + (size_t)db * cells + (cells - 1 - j));
+                constexpr int CG = C / G;
+                const size_t o = ((size_t)db * C + grp * CG) * cells + dc;
+                const float *src = p.bev + o;
+                float *dst = p.out + o;
+#pragma unroll 1
+                for (int c = 0; c < CG; c += kCopyBatch) {   // kCopyBatch loads in flight per thread, then the stores
+                    float v[kCopyBatch];
+#pragma unroll
+                    for (int i = 0; i < kCopyBatch; ++i) {
+                        v[i] = __ldcs(src);
+                        src += cells;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kCopyBatch; ++i) {
+                        __stcs(dst, v[i]);
+                        dst += cells;
                     }
                 }
             }
         }
-        // no barrier here: the tile header state (indices, centres, round count) is double-buffered by tile parity, and
-        // every other shared / tensor-memory buffer is only rewritten behind the next tile's first barrier
-        tc::fence_before_sync();
     }
 
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);
 }
+
 // ---------------------------------------------------------------------------------------------------------------
 // K-4a on tensor cores:  T[b, m, :] = feat[b, m, :] W1[:, :Ci]^T + W1[:, Ci:Ci+3] p_m + b1      (m < num_points[b])
 // Tile = 128 points.  W1's image part stays resident in shared memory; the rank-3 offset term and the bias are

@@ -235,6 +235,18 @@ __device__ __forceinline__ void sts_u32x4(uint32_t addr, const uint4 &v)
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// Ampere-style asynchronous 4-byte copy global -> shared (no register staging); completion via commit / wait_all
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 process two fp32 lanes per issue slot) -----------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
 {

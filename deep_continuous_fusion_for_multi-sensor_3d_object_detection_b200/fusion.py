@@ -119,15 +119,16 @@ class FrameContext:
             torch.cuda.current_stream(self.points.device).wait_event(ev)
 
 
-def fuse_scales(frames, layers, bevs):
+def fuse_scales(frames, layers, bevs, inplace=False):
     """Fuse several backbone scales of one batch at once (inference): tables and KNN ahead on side streams, then one
-    stream per scale, joined before returning.  Returns the fused maps in order."""
+    stream per scale, joined before returning.  Returns the fused maps in order (`inplace=True`: the inputs, updated
+    in place -- the cells without a LiDAR point in reach then cost no memory traffic at all)."""
     dev = frames.points.device
     main = torch.cuda.current_stream(dev)
     with torch.no_grad():
         frames.precompute(layers, [tuple(b.shape[-2:]) for b in bevs])
         frames.wait_knn()
-        outs = [torch.empty_like(b) for b in bevs]
+        outs = list(bevs) if inplace else [torch.empty_like(b) for b in bevs]
         streams = frames._side_streams(len(layers) + 1)[1:]
         for layer, bev, out, st in zip(layers, bevs, outs, streams):
             st.wait_stream(main)

@@ -37,8 +37,8 @@ def oracle_knn(oracle, wl, scale, radius=None, k=None):
                                            dx, dy, r * r, k or wl["k"]) for b in range(wl["points"].shape[0])])
 
 
-def cuda_fusion(dcf, wl, mode, use_uv=False, channels_last=False):
-    """Product path through the nn.Module: returns [out per scale], [knn per scale]."""
+def cuda_fusion(dcf, wl, mode, use_uv=False, channels_last=False, inplace=False):
+    """Product path through the nn.Module: returns [out per scale], [knn per scale].  inplace: out aliases bev."""
     pts, cnt = dev(wl["points"]), dev(wl["num_points"])
     img = dev(wl["img_feat"])
     if channels_last:
@@ -54,7 +54,9 @@ def cuda_fusion(dcf, wl, mode, use_uv=False, channels_last=False):
             layer.fc1.weight.copy_(dev(w1)); layer.fc1.bias.copy_(dev(b1))
             layer.fc2.weight.copy_(dev(w2)); layer.fc2.bias.copy_(dev(b2))
             layer.fc3.weight.copy_(dev(w3)); layer.fc3.bias.copy_(dev(b3))
-            out, knn = layer(dev(sc["bev"]), frames=frames, return_knn=True)
+            bev = dev(sc["bev"])
+            out, knn = layer(bev, frames=frames, return_knn=True, out=bev if inplace else None)
+            assert (out.data_ptr() == bev.data_ptr()) == bool(inplace)
         outs.append(out.cpu().numpy())
         knns.append(knn.cpu().numpy())
     torch.cuda.synchronize()

@@ -41,6 +41,38 @@ def test_fusion_all_five_scales_yaml_grid(dcf, oracle, mode):
     _compare(wl, outs, knns, ref_outs, ref_knns, TOL[mode])
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_fusion_in_place_equals_out_of_place(dcf, mode):
+    """out may alias bev (inference): same bits as the out-of-place call, on the compacted and the plain tile path."""
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=2, k=5), seed=17)
+    a, _ = cuda_fusion(dcf, wl, mode)
+    b, _ = cuda_fusion(dcf, wl, mode, inplace=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_fuse_scales_matches_per_layer_calls(dcf):
+    """fuse_scales (side streams, memcpy + in-place layer) returns what the layers return one by one, and leaves bev intact."""
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=2, k=3), seed=18)
+    ref, _ = cuda_fusion(dcf, wl, "fp32")
+    pts, cnt, img = dev(wl["points"]), dev(wl["num_points"]), dev(wl["img_feat"])
+    frames = dcf.prepare_frames(pts, cnt, img, config=wl["config"], calib=wl["calib"])
+    layers, bevs = [], []
+    for sc in wl["scales"]:
+        layer = dcf.ContinuousFusion(img.shape[1], sc["C"], k=wl["k"], radius=wl["radius"], geom=sc["geom"], mode="fp32").cuda()
+        with torch.no_grad():
+            for prm, w in zip((layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
+                               layer.fc3.bias), sc["weights"]):
+                prm.copy_(dev(w))
+        layers.append(layer.eval())
+        bevs.append(dev(sc["bev"]))
+    outs = dcf.fuse_scales(frames, layers, bevs)
+    torch.cuda.synchronize()
+    for sc, o, r, bv in zip(wl["scales"], outs, ref, bevs):
+        assert np.array_equal(o.cpu().numpy(), r)
+        assert np.array_equal(bv.cpu().numpy(), sc["bev"])
+
+
 def test_fusion_channels_last_map_equals_nchw(dcf):
     wl = dcf.synthetic.make_workload("tiny", seed=14, c_img=64, img_hw=(30, 40))
     a, _ = cuda_fusion(dcf, wl, "simt", channels_last=False)

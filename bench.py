@@ -214,11 +214,13 @@ class GpuPipeline:
             feat, _ = timed("cf_point_gather", lambda: ops.point_gather(self.img, self.points, self.counts, calib=self.calib,
                                                                         img_size=self.size))
             fine, fine_stride = None, 1
-            for sc, layer, bev in zip(self.wl["scales"], self.layers, self.bev):
+            packed1 = [l._packed.w1(l.fc1.weight, self.mode) for l in self.layers]
+            Ts = timed("cf_point_mlp1_multi", lambda: ops.point_mlp1_multi(feat, self.points, self.counts,
+                                                                           [l.fc1.weight for l in self.layers],
+                                                                           [l.fc1.bias for l in self.layers], packed1,
+                                                                           mode=self.mode))
+            for sc, layer, bev, T in zip(self.wl["scales"], self.layers, self.bev, Ts):
                 g = sc["group"]
-                T = timed(f"cf_point_mlp1[g{g}]", lambda: ops.point_mlp1(feat, self.points, self.counts, layer.fc1.weight,
-                                                                         layer.fc1.bias, mode=self.mode,
-                                                                         packed=layer._packed.w1(layer.fc1.weight, self.mode)))
                 if fine is None:
                     knn = timed(f"cf_knn_query[g{g}]", lambda: ops.knn_query(start, srt, self.grid, sc["H"], sc["W"],
                                                                              sc["geom"], self.wl["radius"], self.wl["k"]))

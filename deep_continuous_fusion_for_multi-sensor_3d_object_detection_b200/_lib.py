@@ -34,6 +34,8 @@ SIGNATURES = {
     "cf_point_mlp1_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "cf_point_mlp1": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "cf_point_mlp1_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "cf_point_mlp1_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp),
+                                      C.POINTER(_vp), _i32, C.POINTER(_vp), _vp]),
     "cf_fusion_packed_bytes": (_sz, [_i32, _i32]),
     "cf_fusion_pack_weights": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "cf_fusion_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),

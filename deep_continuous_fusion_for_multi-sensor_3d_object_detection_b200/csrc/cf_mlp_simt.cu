@@ -235,6 +235,10 @@ int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_n
                   int32_t Ci, int32_t C, const float *d_W1, const float *d_b1, float *d_T, int32_t mode,
                   const void *d_packed, void *d_workspace, cudaStream_t st);
 int point_mlp1_tc_pack(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, cudaStream_t st);
+int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
+                        int32_t Ci, int32_t n_scales, const int32_t *h_C, const float *const *h_W1,
+                        const float *const *h_b1, float *const *h_T, int32_t mode, const void *const *h_packed,
+                        cudaStream_t st);
 }  // namespace cf
 
 extern "C" int cf_point_mlp1_pack_weights(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, void *stream)
@@ -271,4 +275,26 @@ extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const i
         if (rc != CF_ERR_UNSUPPORTED) return rc;  // shapes without a tensor-core instantiation use the FFMA kernel
     }
     return point_mlp1_simt(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, (cudaStream_t)stream);
+}
+
+extern "C" int cf_point_mlp1_multi(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
+                                   int32_t N, int32_t Ci, int32_t n_scales, const int32_t *h_C,
+                                   const float *const *h_W1, const float *const *h_b1, float *const *h_T, int32_t mode,
+                                   const void *const *h_packed, void *stream)
+{
+    using namespace cf;
+    CF_TRY(require_sm100());
+    CF_REQUIRE(d_feat && d_points && d_num_points && h_C && h_W1 && h_b1 && h_T && h_packed, CF_ERR_ARG,
+               "cf_point_mlp1_multi: null pointer");
+    CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && Ci > 0 && n_scales > 0, CF_ERR_ARG, "cf_point_mlp1_multi: bad extents");
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_point_mlp1_multi: mode %d has no tensor-core path", mode);
+    CF_REQUIRE(aligned16(d_feat), CF_ERR_ALIGN, "cf_point_mlp1_multi: feat must be 16-byte aligned");
+    for (int s = 0; s < n_scales && s < 64; ++s) {
+        CF_REQUIRE(h_W1[s] && h_b1[s] && h_T[s] && h_packed[s], CF_ERR_ARG, "cf_point_mlp1_multi: null pointer for scale %d", s);
+        CF_REQUIRE(aligned16(h_T[s]) && aligned16(h_packed[s]), CF_ERR_ALIGN, "cf_point_mlp1_multi: T / packed weights of scale %d must be 16-byte aligned", s);
+    }
+    const int rc = point_mlp1_multi_tc(d_feat, d_points, d_num_points, B, N, Ci, n_scales, h_C, h_W1, h_b1, h_T, mode,
+                                       h_packed, (cudaStream_t)stream);
+    if (rc == CF_ERR_UNSUPPORTED) set_error("cf_point_mlp1_multi: shapes not supported by the multi-scale kernel (Ci=%d, %d scales)", Ci, n_scales);
+    return rc;
 }

@@ -796,6 +796,182 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
     if (warp == 0) tc::tmem_free(tmem_acc, kCols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-4a for SEVERAL scales in one pass.  The camera features of a 128-point tile are split and packed into the UMMA A
+// operand ONCE, then multiplied by every scale's W1 image part: the output channels of all scales form one long N
+// dimension that is walked in chunks of <= 128 columns.  Per chunk: the packed weight rows stream L2 -> shared memory
+// into one of two buffers, one thread issues the K = Ci MMAs into one of two TMEM accumulators, and the epilogue of the
+// previous chunk (rank-3 offset + bias, write T) runs under them.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxScales = 8, kMaxChunks = 16;
+struct Mlp1MultiParams {
+    const float *feat;
+    const float *points;
+    const int64_t *num_points;
+    int32_t B, N, Ci, tiles_per_frame, n_scales, n_chunks;
+    const uint8_t *wimg[kMaxScales];
+    const float *W1[kMaxScales];
+    const float *b1[kMaxScales];
+    float *T[kMaxScales];
+    int32_t C[kMaxScales], foff[kMaxScales];   // channels; offset (floats) of the scale's b1|wx|wy|wz table in shared memory
+    int32_t chunk_scale[kMaxChunks], chunk_n0[kMaxChunks], chunk_len[kMaxChunks];
+};
+
+template <int NS>
+__global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
+{
+    constexpr int NT = 256, NW = NT / 32;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int Ci = p.Ci, kc_units = Ci / 8;
+    const int a_bytes = NS * kTile * Ci * 2, w_bytes = NS * kTile * Ci * 2;
+    uint8_t *sA = smem;
+    uint8_t *sWb = smem + a_bytes;                        // two buffers of w_bytes
+    float *sF = reinterpret_cast<float *>(smem + a_bytes + 2 * w_bytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (kTile - 1), half = tid / kTile;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar[0], 1);
+        tc::mbar_init(&bar[1], 1);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+    for (int s = 0; s < p.n_scales; ++s) {
+        const int C = p.C[s];
+        float *f = sF + p.foff[s];
+        for (int c = tid; c < C; c += NT) {
+            const float *w = p.W1[s] + (size_t)c * (Ci + 3) + Ci;
+            f[c] = __ldg(p.b1[s] + c);
+            f[C + c] = __ldg(w);
+            f[2 * C + c] = __ldg(w + 1);
+            f[3 * C + c] = __ldg(w + 2);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sWb);
+    const uint32_t sbo = kc_units * 128, lbo = 128;
+    uint32_t ph0 = 0, ph1 = 0;
+
+    const int64_t tiles_total = (int64_t)p.tiles_per_frame * p.B;
+    for (int64_t tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+        const int b = (int)(tile / p.tiles_per_frame);
+        const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
+        const int32_t n_pts = valid_points(p.num_points, b, p.N);
+        if (m0 >= n_pts) continue;  // uniform across the CTA
+        // ---- A tile, once for all scales (same lane mapping as k_point_mlp1_tc) -----------------------------------------
+        const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
+        for (int item = warp; item < 16 * (kc_units / 4); item += NW) {
+            const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
+            const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
+            float v[8];
+            if (m0 + r < n_pts) {
+                const float4 *src = reinterpret_cast<const float4 *>(fb + (size_t)r * Ci + ku * 8);
+                const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            }
+            uint4 hi, lo;
+            tc::split_bf16x8(v, hi, lo, NS == 2);
+            const uint32_t off = tc::unit_offset(r, ku, kc_units);
+            *reinterpret_cast<uint4 *>(sA + off) = hi;
+            if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Ci * 2 + off) = lo;
+        }
+        const int32_t m = m0 + row;
+        const bool live = m < n_pts;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (live) {
+            const float *q = p.points + ((size_t)b * p.N + m) * 3;
+            px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+        }
+        // epilogue of chunk j: T_s[m, n0 + c] = acc + W1[:, Ci:Ci+3] p + b1
+        auto epilogue = [&](int j) {
+            const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], len = p.chunk_len[j], C = p.C[s];
+            const float *f = sF + p.foff[s];
+            const uint32_t acc = tmem_base + (uint32_t)((j & 1) * kTile) + lane_off;
+            float *trow = p.T[s] + ((size_t)b * p.N + m) * C + n0;
+#pragma unroll 1
+            for (int c = half * 16; c < len; c += 32) {
+                float z[16];
+                tc::tmem_ld16(acc + c, z);
+                if (live) {
+                    float4 *dst = reinterpret_cast<float4 *>(trow + c);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int n = n0 + c + q4 * 4 + i;
+                            o[i] = z[q4 * 4 + i] + (f[C + n] * px + f[2 * C + n] * py + f[3 * C + n] * pz) + f[n];
+                        }
+                        dst[q4] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+        };
+        for (int j = 0; j < p.n_chunks; ++j) {
+            const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], len = p.chunk_len[j];
+            // the chunk's rows of the packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes)
+            {
+                const int piece = len * Ci * 2;
+                const uint8_t *src = p.wimg[s] + (size_t)(n0 / 8) * kc_units * 128;
+                uint8_t *dst = sWb + (j & 1) * w_bytes;
+                for (int o = tid * 16; o < piece; o += NT * 16) {
+                    *reinterpret_cast<uint4 *>(dst + o) = __ldg(reinterpret_cast<const uint4 *>(src + o));
+                    if (NS == 2)
+                        *reinterpret_cast<uint4 *>(dst + kTile * Ci * 2 + o) =
+                            __ldg(reinterpret_cast<const uint4 *>(src + (size_t)p.C[s] * Ci * 2 + o));
+                }
+            }
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+                const uint32_t idesc = tc::make_idesc_bf16(kTile, len);
+                const uint32_t w0 = sW_addr + (uint32_t)((j & 1) * w_bytes), acc = tmem_base + (uint32_t)((j & 1) * kTile);
+                uint32_t accum = 0;
+                for (int kk = 0; kk < Ci / 16; ++kk) {
+                    const uint32_t koff = kk * 2 * lbo;
+                    const uint64_t a_hi = tc::make_desc(sA_addr + koff, lbo, sbo), w_hi = tc::make_desc(w0 + koff, lbo, sbo);
+                    tc::mma_bf16(acc, a_hi, w_hi, idesc, accum);
+                    accum = 1;
+                    if (NS == 2) {
+                        const uint64_t a_lo = tc::make_desc(sA_addr + kTile * Ci * 2 + koff, lbo, sbo);
+                        const uint64_t w_lo = tc::make_desc(w0 + kTile * Ci * 2 + koff, lbo, sbo);
+                        tc::mma_bf16(acc, a_hi, w_lo, idesc, 1);
+                        tc::mma_bf16(acc, a_lo, w_hi, idesc, 1);
+                    }
+                }
+                tc::commit(&bar[j & 1]);
+            }
+            if (j > 0) {   // the previous chunk's epilogue runs under this chunk's MMAs
+                if ((j - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+                tc::fence_after_sync();
+                epilogue(j - 1);
+            }
+        }
+        {
+            const int j = p.n_chunks - 1;
+            if (j & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+            tc::fence_after_sync();
+            epilogue(j);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_free(tmem_base, 256);
+}
+
 template <int C, int NS>
 int launch_mlp1_tc(const Mlp1Params &p, cudaStream_t st)
 {
@@ -1034,6 +1210,45 @@ int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_n
     CF_TRY(rc);
     count_launches(1);
     return launch_status("cf_point_mlp1 (tcgen05)");
+}
+
+// returns CF_ERR_UNSUPPORTED (without setting an error) when the shapes do not fit the multi-scale kernel
+int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
+                        int32_t Ci, int32_t n_scales, const int32_t *h_C, const float *const *h_W1,
+                        const float *const *h_b1, float *const *h_T, int32_t mode, const void *const *h_packed,
+                        cudaStream_t st)
+{
+    const int NS = mode == CF_MODE_FP32 ? 2 : 1;
+    if (n_scales < 1 || n_scales > kMaxScales || Ci % 32 != 0 || Ci > 256) return CF_ERR_UNSUPPORTED;
+    Mlp1MultiParams p;
+    p.feat = d_feat; p.points = d_points; p.num_points = d_num_points;
+    p.B = B; p.N = N; p.Ci = Ci; p.tiles_per_frame = (N + kTile - 1) / kTile; p.n_scales = n_scales;
+    int chunks = 0, foff = 0;
+    for (int s = 0; s < n_scales; ++s) {
+        const int C = h_C[s];
+        if (C % 32 != 0 || C < 32 || C > 1024 || !h_packed[s]) return CF_ERR_UNSUPPORTED;
+        p.wimg[s] = (const uint8_t *)h_packed[s]; p.W1[s] = h_W1[s]; p.b1[s] = h_b1[s]; p.T[s] = h_T[s];
+        p.C[s] = C; p.foff[s] = foff;
+        foff += 4 * C;
+        for (int n0 = 0; n0 < C; n0 += kTile) {
+            if (chunks == kMaxChunks) return CF_ERR_UNSUPPORTED;
+            p.chunk_scale[chunks] = s; p.chunk_n0[chunks] = n0; p.chunk_len[chunks] = std::min(kTile, C - n0);
+            ++chunks;
+        }
+    }
+    p.n_chunks = chunks;
+    const size_t smem = (size_t)3 * NS * kTile * Ci * 2 + (size_t)foff * 4;
+    if (smem > 225 * 1024) return CF_ERR_UNSUPPORTED;
+    auto kern = NS == 2 ? k_point_mlp1_multi<2> : k_point_mlp1_multi<1>;
+    CF_TRY(cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "k_point_mlp1_multi smem attribute"));
+    const int64_t tiles = (int64_t)p.tiles_per_frame * B;
+    // one CTA per SM (shared memory); an even share of tiles per CTA beats leaving a few CTAs with one tile more
+    const int64_t waves = ceil_div64(tiles, sm_count());
+    const int64_t grid = std::max<int64_t>(1, ceil_div64(tiles, waves));
+    kern<<<(unsigned)grid, 256, smem, st>>>(p);
+    count_launches(1);
+    return launch_status("cf_point_mlp1_multi (tcgen05)");
 }
 
 int umma_selftest(const float *d_A, const float *d_B, int32_t N, int32_t Kd, int32_t split, float *d_D, cudaStream_t st)

@@ -83,8 +83,26 @@ class FrameContext:
         ready = torch.cuda.Event()
         ready.record(main)
         streams = self._side_streams(len(layers) + 1)
-        for layer, st in zip(layers, streams[1:]):
-            T = torch.empty((self.B, self.N, layer.c_bev), dtype=torch.float32, device=self.points.device)
+        dev = self.points.device
+        Ci = self.feat.shape[2]
+        multi = (len(layers) > 1 and len(layers) <= 8 and Ci % 32 == 0 and Ci <= 128 and len({l.mode for l in layers}) == 1
+                 and layers[0].mode in ("fp32", "bf16") and all(l.c_bev % 32 == 0 for l in layers)
+                 and sum(-(-l.c_bev // 128) for l in layers) <= 16)
+        if multi:
+            # one launch for every scale: the point features are packed into the tensor-core operand once
+            Ts = [torch.empty((self.B, self.N, l.c_bev), dtype=torch.float32, device=dev) for l in layers]
+            packed = [l._packed.w1(l.fc1.weight, l.mode) for l in layers]   # packs on the current (main) stream if stale
+            st = streams[1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st), torch.no_grad():
+                ops.point_mlp1_multi(self.feat, self.points, self.num_points, [l.fc1.weight for l in layers],
+                                     [l.fc1.bias for l in layers], packed, mode=layers[0].mode, outs=Ts)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            for l, T in zip(layers, Ts):
+                self._tables[id(l)] = (T, ev)
+        for layer, st in zip([] if multi else layers, streams[1:]):
+            T = torch.empty((self.B, self.N, layer.c_bev), dtype=torch.float32, device=dev)
             packed = layer._packed.w1(layer.fc1.weight, layer.mode)   # packs on the current (main) stream if stale
             st.wait_stream(main)
             with torch.cuda.stream(st), torch.no_grad():

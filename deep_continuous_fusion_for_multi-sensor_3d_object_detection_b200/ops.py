@@ -192,6 +192,33 @@ def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspac
     return out
 
 
+def point_mlp1_multi(feat, points, num_points, W1s, b1s, packeds, mode="fp32", outs=None):
+    """K-4a for several scales in ONE launch (cf_point_mlp1_multi): the point features are packed into the tensor-core
+    operand once and multiplied by every scale's W1.  `packeds` = the scales' packed W1 images (PackedWeights.w1).
+    Returns the list of T (B,N,C_s), identical to per-scale point_mlp1 calls."""
+    import ctypes as C
+    lib = load()
+    feat = _contig(feat, "feat", torch.float32, 3)
+    points = _contig(points, "points", torch.float32, 3)
+    B, N, Ci = feat.shape
+    n = len(W1s)
+    W1s = [_contig(w, "W1", torch.float32, 2) for w in W1s]
+    b1s = [_contig(b, "b1", torch.float32, 1) for b in b1s]
+    for w, b in zip(W1s, b1s):
+        if w.shape[1] != Ci + 3 or b.shape[0] != w.shape[0]:
+            raise ValueError(f"W1/b1: expected (C,{Ci + 3})/(C,), got {tuple(w.shape)}/{tuple(b.shape)}")
+    if len(b1s) != n or len(packeds) != n or any(pk is None for pk in packeds):
+        raise ValueError("point_mlp1_multi: one W1, b1 and packed image per scale")
+    if outs is None:
+        outs = [torch.empty((B, N, w.shape[0]), dtype=torch.float32, device=feat.device) for w in W1s]
+    m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    hC = (C.c_int32 * n)(*[int(w.shape[0]) for w in W1s])
+    check(lib.cf_point_mlp1_multi(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, n, hC, arr(W1s), arr(b1s), arr(outs), m,
+                                  arr(packeds), stream_ptr()), "cf_point_mlp1_multi")
+    return outs
+
+
 def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None, workspace=None, packed=None):
     """K-4.  out = bev + W3 sum_k relu(W2 relu(T[idx_k] - e_cell) + b2) + n_valid b3."""
     lib = load()

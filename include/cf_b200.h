@@ -116,6 +116,15 @@ CF_API int cf_point_mlp1(const float *d_feat, const float *d_points, const int64
  * not change between calls (inference) packs them once into a buffer of cf_point_mlp1_workspace_bytes /
  * cf_fusion_packed_bytes bytes and passes it as d_packed; with d_packed == NULL every call packs into d_workspace. */
 CF_API int cf_point_mlp1_pack_weights(const float *d_W1, int32_t Ci, int32_t C, int32_t mode, void *d_packed, void *stream);
+/* K-4a for several scales in one launch: the point features are packed into the tensor-core operand once and
+ * multiplied by every scale's W1.  h_* are HOST arrays of n_scales entries (channel counts and DEVICE pointers):
+ * h_W1[s] (C_s, Ci+3), h_b1[s] (C_s), h_T[s] (B,N,C_s) out, h_packed[s] from cf_point_mlp1_pack_weights (required).
+ * Same result as n_scales calls of cf_point_mlp1 in the same mode.  Ci % 32 == 0, C_s % 32 == 0, n_scales <= 8;
+ * CF_ERR_UNSUPPORTED if the shapes do not fit (call cf_point_mlp1 per scale instead). */
+CF_API int cf_point_mlp1_multi(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B,
+                        int32_t N, int32_t Ci, int32_t n_scales, const int32_t *h_C, const float *const *h_W1,
+                        const float *const *h_b1, float *const *h_T, int32_t mode, const void *const *h_packed,
+                        void *stream);
 CF_API size_t cf_fusion_packed_bytes(int32_t C, int32_t mode);
 CF_API int cf_fusion_pack_weights(const float *d_W2, const float *d_W3, int32_t C, int32_t mode, void *d_packed,
                            void *stream);

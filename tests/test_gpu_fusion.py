@@ -73,6 +73,27 @@ def test_fuse_scales_matches_per_layer_calls(dcf):
         assert np.array_equal(bv.cpu().numpy(), sc["bev"])
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_point_mlp1_multi_equals_per_scale_calls(dcf, mode):
+    """cf_point_mlp1_multi (one launch, A operand packed once) == cf_point_mlp1 per scale, bit for bit, incl. ragged frames."""
+    torch.manual_seed(19)
+    B, N, Ci = 3, 1000, 128
+    feat = torch.randn(B, N, Ci, device="cuda")
+    pts = torch.randn(B, N, 3, device="cuda") * 20
+    cnt = torch.tensor([1000, 0, 517], dtype=torch.int64, device="cuda")
+    Cs = [32, 64, 128, 192, 256]
+    W1s = [torch.randn(c, Ci + 3, device="cuda") * 0.1 for c in Cs]
+    b1s = [torch.randn(c, device="cuda") for c in Cs]
+    pks = [dcf.ops.PackedWeights().w1(w, mode) for w in W1s]
+    multi = dcf.ops.point_mlp1_multi(feat, pts, cnt, W1s, b1s, pks, mode=mode,
+                                     outs=[torch.zeros(B, N, c, device="cuda") for c in Cs])
+    for w, b, pk, tm, c in zip(W1s, b1s, pks, multi, Cs):
+        one = dcf.ops.point_mlp1(feat, pts, cnt, w, b, mode=mode, packed=pk, out=torch.zeros(B, N, c, device="cuda"))
+        torch.cuda.synchronize()
+        assert torch.equal(one, tm)
+        assert one[0].abs().max() > 0 and float(tm[1].abs().max()) == 0.0 and float(tm[2, 517:].abs().max()) == 0.0
+
+
 def test_fusion_channels_last_map_equals_nchw(dcf):
     wl = dcf.synthetic.make_workload("tiny", seed=14, c_img=64, img_hw=(30, 40))
     a, _ = cuda_fusion(dcf, wl, "simt", channels_last=False)

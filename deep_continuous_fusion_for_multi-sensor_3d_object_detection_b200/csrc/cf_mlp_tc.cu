@@ -70,6 +70,9 @@ __host__ __device__ constexpr int kc_for(int C, int NS)
 #ifndef CF_PIPE
 #define CF_PIPE 1
 #endif
+#ifndef CF_PIPE_MAXC
+#define CF_PIPE_MAXC 128
+#endif
 #ifndef CF_G32
 #define CF_G32 1
 #define CF_G64 2
@@ -102,7 +105,7 @@ struct TcLayout {
     static constexpr int kChunks = C / KC;
     static_assert(C % KC == 0 && KC % 32 == 0, "channel count must be a multiple of the K-chunk");
     static constexpr int kWChunkBytes = NS * C * KC * 2;            // one K-chunk of one layer, all splits
-    static constexpr int kWBytes = kResident ? 2 * kWChunkBytes : kWChunkBytes;
+    static constexpr int kWBytes = 2 * kWChunkBytes;                // resident: W2 | W3;  streamed: two chunk buffers
     static constexpr int kABytes = NS * kTile * KC * 2;             // one A tile (all splits)
     static constexpr int kOffA = kWBytes;
     static constexpr int kOffAb = kOffA + kABytes;                  // bias A operand: 128 rows x 16 bf16 (2 units / row)
@@ -280,9 +283,19 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
         const uint32_t packed = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
         *reinterpret_cast<uint32_t *>(sWb + layer * L::kWbBytes + tc::unit_offset(c, 0, 2)) = packed;
     }
+    // Streamed weights (C > 128): chunks of KC input channels travel L2 -> shared memory with cp.async into two
+    // buffers, always one chunk ahead of the MMAs; `wn` counts the chunks consumed so far (buffer = wn & 1).
+    uint32_t wn = 0;
+    auto prefetch_wchunk = [&](const uint8_t *src, uint32_t buf) {
+        const uint32_t dst = tc::smem_u32(sW) + buf * L::kWChunkBytes;
+        for (int o = tid * 16; o < L::kWChunkBytes; o += NT * 16) tc::cp_async16(dst + o, src + o);
+        tc::cp_async_commit();
+    };
     if (L::kResident) {
         copy_chunk<NT>(sW, p.wimg2, L::kWChunkBytes);
         copy_chunk<NT>(sW + L::kWChunkBytes, p.wimg3, L::kWChunkBytes);
+    } else {
+        prefetch_wchunk(p.wimg2, 0);
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             // Pipelined shapes (both layers resident, 4 items per warp and round): tv holds the gathered neighbour rows
             // of the NEXT round while this round's MMA and epilogue run; in the last round the same 32 registers take the
             // bev values of this thread's first two output chunks instead.
-            constexpr bool kPipe = CF_PIPE && kEven && L::kChunks == 1 && kItems == 4;
+            constexpr bool kPipe = CF_PIPE && C <= CF_PIPE_MAXC && kEven && L::kChunks == 1 && kItems == 4;
             constexpr int kPre = kPipe ? 2 : 0;   // output chunks whose bev values are prefetched
             float tv[32];
             auto prefetch_bev = [&]() {
@@ -453,7 +466,6 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             for (int k = 0; k < R; ++k) {
                 const uint32_t idxk = idx0 + (uint32_t)(k * kTile * 4);
                 for (int ch = 0; ch < L::kChunks; ++ch) {
-                    if (!L::kResident) copy_chunk<NT>(sW, p.wimg2 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
                     if (kPipe) {
                         load_offset_weights(0);
                         // rows were gathered while the previous round's MMA and epilogue ran
@@ -484,6 +496,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     }
                     if (ch == 0 && grp == 0)   // bias flag of the row: bf16 (1, 1) or (0, 0)
                         tc::sts_u32(ab_row, (int32_t)tc::lds_u32(sidx_addr + (uint32_t)(((par * K + k) * kTile + row) * 4)) >= 0 ? 0x3F803F80u : 0u);
+                    if (!L::kResident) tc::cp_async_wait_all();   // this thread's part of the weight chunk has landed
                     tc::fence_proxy_async();
                     tc::fence_before_sync();
                     __syncthreads();
@@ -491,8 +504,16 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         tc::fence_after_sync();
                         if (ch == 0)
                             tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr, 128, 256), idesc, 0u);
-                        issue_chunk<C, NS, KC>(sA_addr, sW_addr, tmem_acc, true);
+                        issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? 0 : (wn & 1) * L::kWChunkBytes), tmem_acc, true);
                         tc::commit(bar);
+                    }
+                    if (!L::kResident) {
+                        // next chunk in the tile's fixed sequence: W2 chunks of every round, then the W3 chunks
+                        const uint8_t *nsrc = ch + 1 < L::kChunks ? p.wimg2 + (size_t)(ch + 1) * L::kWChunkBytes
+                                              : k + 1 < R        ? p.wimg2
+                                                                 : p.wimg3;
+                        ++wn;
+                        prefetch_wchunk(nsrc, wn & 1);   // its buffer was last read by the previous chunk's MMAs, already complete
                     }
                     if (ch == L::kChunks - 1) {
                         // work that overlaps this round's MMA and epilogue: the next tile's header, then the next round's
@@ -538,7 +559,6 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             if (R > 0) {
                 // ---- layer 3: acc = n_valid * b3 + pooled * W3^T -----------------------------------------------------------
                 for (int ch = 0; ch < L::kChunks; ++ch) {
-                    if (!L::kResident) copy_chunk<NT>(sW, p.wimg3 + (size_t)ch * L::kWChunkBytes, L::kWChunkBytes);
                     __syncwarp();
 #pragma unroll 1
                     for (int cc = grp; cc < KC / EW; cc += G) {
@@ -560,6 +580,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         const uint32_t nv16 = __float_as_uint((float)n_valid) >> 16;   // small integers are exact in bf16
                         tc::sts_u32(ab_row, nv16 | (nv16 << 16));
                     }
+                    if (!L::kResident) tc::cp_async_wait_all();
                     tc::fence_proxy_async();
                     tc::fence_before_sync();
                     __syncthreads();
@@ -568,8 +589,13 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         if (ch == 0)
                             tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr + L::kWbBytes, 128, 256),
                                          idesc, 0u);
-                        issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : 0), tmem_acc, true);
+                        issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : (wn & 1) * L::kWChunkBytes), tmem_acc, true);
                         tc::commit(bar);
+                    }
+                    if (!L::kResident) {   // next: the following W3 chunk, or the first W2 chunk for the next tile
+                        const uint8_t *nsrc = ch + 1 < L::kChunks ? p.wimg3 + (size_t)(ch + 1) * L::kWChunkBytes : p.wimg2;
+                        ++wn;
+                        prefetch_wchunk(nsrc, wn & 1);
                     }
                     tc::mbar_wait(bar, phase);
                     phase ^= 1u;
@@ -643,6 +669,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
         }
     }
 
+    tc::cp_async_wait_all();   // the weight chunk prefetched for a tile that never came
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);

@@ -25,12 +25,21 @@ class FrameContext:
         self.B, self.N = self.points.shape[:2]
         self.num_points = ops.as_counts(num_points, self.B, self.points.device)
         self.grid = grid
-        self.bucket_start, self.sorted_pts, self._bucket_ws = ops.bucket_points(self.points, self.num_points, grid)
         self.feat = None
         self._gather_ws = None
         self._knn_cache = {}
         self._tables = {}      # id(layer) -> (T, ready event): per-scale point tables computed ahead on side streams
         self._streams = []
+        # K-1 runs on a side stream: the camera-feature gather (K-3) does not depend on it, only the KNN search does
+        main = torch.cuda.current_stream(self.points.device)
+        st = self._side_streams(1)[0]
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            self.bucket_start, self.sorted_pts, self._bucket_ws = ops.bucket_points(self.points, self.num_points, grid)
+            self._bucket_done = torch.cuda.Event()
+            self._bucket_done.record(st)
+        for t in (self.bucket_start, self.sorted_pts, self._bucket_ws):
+            t.record_stream(main)
 
     def gather(self, img_feat, calib=None, uv=None, img_size=(640.0, 480.0)):
         if torch.is_grad_enabled() and img_feat.requires_grad:
@@ -59,6 +68,7 @@ class FrameContext:
                         and (H - 1) * m < Hf and (W - 1) * m < Wf):
                     self._knn_cache[key] = ops.knn_subsample(fine, m, H, W)
                     return self._knn_cache[key]
+        torch.cuda.current_stream(self.points.device).wait_event(self._bucket_done)
         self._knn_cache[key] = ops.knn_query(self.bucket_start, self.sorted_pts, self.grid, H, W, geom, radius, K)
         return self._knn_cache[key]
 
@@ -80,8 +90,6 @@ class FrameContext:
         if self.feat is None:
             raise ValueError("FrameContext.precompute: call gather() first")
         main = torch.cuda.current_stream(self.points.device)
-        ready = torch.cuda.Event()
-        ready.record(main)
         streams = self._side_streams(len(layers) + 1)
         dev = self.points.device
         Ci = self.feat.shape[2]
@@ -112,12 +120,14 @@ class FrameContext:
                 ev.record(st)
             self._tables[id(layer)] = (T, ev)
         if shapes is not None:
+            # The search runs on the bucketing stream (it only needs K-1, not the gather).  Only the largest map is
+            # searched here; tables of nested coarser scales are strided copies of it, made by each layer on its own
+            # stream (FrameContext.knn), so they run side by side instead of one after the other.
             st = streams[0]
-            st.wait_event(ready)
             with torch.cuda.stream(st):
-                for layer, (H, W) in zip(layers, shapes):
-                    knn = self.knn(H, W, layer.geom, layer.radius, layer.k)
-                    knn.record_stream(main)
+                big = max(range(len(layers)), key=lambda i: shapes[i][0] * shapes[i][1])
+                knn = self.knn(shapes[big][0], shapes[big][1], layers[big].geom, layers[big].radius, layers[big].k)
+                knn.record_stream(main)
                 ev = torch.cuda.Event()
                 ev.record(st)
             self._knn_ready = ev

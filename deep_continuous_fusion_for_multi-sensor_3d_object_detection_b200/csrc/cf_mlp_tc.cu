@@ -845,9 +845,11 @@ struct Mlp1MultiParams {
 };
 
 template <int NS>
-__global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
+__global__ void __launch_bounds__(288, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
 {
-    constexpr int NT = 256, NW = NT / 32;
+    // warps 0-7: workers (operand build, weight prefetch, epilogues); warp 8: its lane 0 only issues the MMAs, so the
+    // ~70 tcgen05.mma of a chunk never sit in front of a worker warp's epilogue
+    constexpr int NT = 256, NW = NT / 32, kIssuer = 256;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar[2];
     __shared__ uint32_t tmem_slot;
@@ -858,6 +860,7 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
     float *sF = reinterpret_cast<float *>(smem + a_bytes + 2 * w_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), half = tid / kTile;
+    const bool worker = tid < NT;
 
     if (tid == 0) {
         tc::mbar_init(&bar[0], 1);
@@ -868,13 +871,10 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
     for (int s = 0; s < p.n_scales; ++s) {
         const int C = p.C[s];
-        float *f = sF + p.foff[s];
-        for (int c = tid; c < C; c += NT) {
+        float4 *f = reinterpret_cast<float4 *>(sF + p.foff[s]);   // per output channel: (b1, wx, wy, wz)
+        for (int c = tid; c < C; c += NT + 32) {
             const float *w = p.W1[s] + (size_t)c * (Ci + 3) + Ci;
-            f[c] = __ldg(p.b1[s] + c);
-            f[C + c] = __ldg(w);
-            f[2 * C + c] = __ldg(w + 1);
-            f[3 * C + c] = __ldg(w + 2);
+            f[c] = make_float4(__ldg(p.b1[s] + c), __ldg(w), __ldg(w + 1), __ldg(w + 2));
         }
     }
     tc::fence_before_sync();
@@ -885,6 +885,19 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sWb);
     const uint32_t sbo = kc_units * 128, lbo = 128;
     uint32_t ph0 = 0, ph1 = 0;
+    uint32_t cn = 0;   // chunks issued so far: weight buffer, accumulator and mbarrier of a chunk = cn & 1
+    // the chunk's rows of a packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes); cp.async
+    auto prefetch_w = [&](int j, uint32_t buf) {
+        const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], piece = p.chunk_len[j] * Ci * 2;
+        const uint8_t *src = p.wimg[s] + (size_t)(n0 / 8) * kc_units * 128;
+        const uint32_t dst = sW_addr + buf * w_bytes;
+        for (int o = tid * 16; worker && o < piece; o += NT * 16) {
+            tc::cp_async16(dst + o, src + o);
+            if (NS == 2) tc::cp_async16(dst + kTile * Ci * 2 + o, src + (size_t)p.C[s] * Ci * 2 + o);
+        }
+        tc::cp_async_commit();
+    };
+    prefetch_w(0, 0);
 
     const int64_t tiles_total = (int64_t)p.tiles_per_frame * p.B;
     for (int64_t tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
@@ -892,41 +905,56 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
         const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
         const int32_t n_pts = valid_points(p.num_points, b, p.N);
         if (m0 >= n_pts) continue;  // uniform across the CTA
-        // ---- A tile, once for all scales (same lane mapping as k_point_mlp1_tc) -----------------------------------------
+        // ---- A tile, once for all scales (same lane mapping as k_point_mlp1_tc).  The feature rows stream from DRAM:
+        // the loads of a batch of items are all issued before the first one is split and stored ------------------------
         const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
-        for (int item = warp; item < 16 * (kc_units / 4); item += NW) {
-            const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
-            const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
-            float v[8];
-            if (m0 + r < n_pts) {
-                const float4 *src = reinterpret_cast<const float4 *>(fb + (size_t)r * Ci + ku * 8);
-                const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
-                v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-            } else {
+        const int n_items = 16 * (kc_units / 4);
+        constexpr int kBatch = 8;
+        for (int item0 = warp; worker && item0 < n_items; item0 += NW * kBatch) {
+            float4 t0[kBatch], t1[kBatch];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            for (int u = 0; u < kBatch; ++u) {
+                const int item = item0 + u * NW;
+                const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
+                const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
+                t0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                t1[u] = t0[u];
+                if (item < n_items && m0 + r < n_pts) {
+                    const float4 *src = reinterpret_cast<const float4 *>(fb + (size_t)r * Ci + ku * 8);
+                    t0[u] = __ldg(src);
+                    t1[u] = __ldg(src + 1);
+                }
             }
-            uint4 hi, lo;
-            tc::split_bf16x8(v, hi, lo, NS == 2);
-            const uint32_t off = tc::unit_offset(r, ku, kc_units);
-            *reinterpret_cast<uint4 *>(sA + off) = hi;
-            if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Ci * 2 + off) = lo;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int item = item0 + u * NW;
+                if (item < n_items) {
+                    const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
+                    const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
+                    const float v[8] = {t0[u].x, t0[u].y, t0[u].z, t0[u].w, t1[u].x, t1[u].y, t1[u].z, t1[u].w};
+                    uint4 hi, lo;
+                    tc::split_bf16x8(v, hi, lo, NS == 2);
+                    const uint32_t off = tc::unit_offset(r, ku, kc_units);
+                    *reinterpret_cast<uint4 *>(sA + off) = hi;
+                    if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Ci * 2 + off) = lo;
+                }
+            }
         }
         const int32_t m = m0 + row;
-        const bool live = m < n_pts;
+        const bool live = worker && m < n_pts;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (live) {
             const float *q = p.points + ((size_t)b * p.N + m) * 3;
             px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
         }
         // epilogue of chunk j: T_s[m, n0 + c] = acc + W1[:, Ci:Ci+3] p + b1
-        auto epilogue = [&](int j) {
+        auto epilogue = [&](int j, uint32_t buf) {
             const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], len = p.chunk_len[j], C = p.C[s];
-            const float *f = sF + p.foff[s];
-            const uint32_t acc = tmem_base + (uint32_t)((j & 1) * kTile) + lane_off;
+            const float4 *f = reinterpret_cast<const float4 *>(sF + p.foff[s]);
+            const uint32_t acc = tmem_base + buf * kTile + lane_off;
             float *trow = p.T[s] + ((size_t)b * p.N + m) * C + n0;
 #pragma unroll 1
-            for (int c = half * 16; c < len; c += 32) {
+            for (int c = half * 16; worker && c < len; c += 32) {
                 float z[16];
                 tc::tmem_ld16(acc + c, z);
                 if (live) {
@@ -936,8 +964,8 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
                         float o[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int n = n0 + c + q4 * 4 + i;
-                            o[i] = z[q4 * 4 + i] + (f[C + n] * px + f[2 * C + n] * py + f[3 * C + n] * pz) + f[n];
+                            const float4 w = f[n0 + c + q4 * 4 + i];
+                            o[i] = z[q4 * 4 + i] + (w.y * px + w.z * py + w.w * pz) + w.x;
                         }
                         dst[q4] = make_float4(o[0], o[1], o[2], o[3]);
                     }
@@ -946,26 +974,15 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
             tc::fence_before_sync();
         };
         for (int j = 0; j < p.n_chunks; ++j) {
-            const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], len = p.chunk_len[j];
-            // the chunk's rows of the packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes)
-            {
-                const int piece = len * Ci * 2;
-                const uint8_t *src = p.wimg[s] + (size_t)(n0 / 8) * kc_units * 128;
-                uint8_t *dst = sWb + (j & 1) * w_bytes;
-                for (int o = tid * 16; o < piece; o += NT * 16) {
-                    *reinterpret_cast<uint4 *>(dst + o) = __ldg(reinterpret_cast<const uint4 *>(src + o));
-                    if (NS == 2)
-                        *reinterpret_cast<uint4 *>(dst + kTile * Ci * 2 + o) =
-                            __ldg(reinterpret_cast<const uint4 *>(src + (size_t)p.C[s] * Ci * 2 + o));
-                }
-            }
+            const int len = p.chunk_len[j];
+            tc::cp_async_wait_all();   // this thread's part of the chunk's weights has landed (prefetched one chunk ahead)
             tc::fence_proxy_async();
             tc::fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (tid == kIssuer) {
                 tc::fence_after_sync();
                 const uint32_t idesc = tc::make_idesc_bf16(kTile, len);
-                const uint32_t w0 = sW_addr + (uint32_t)((j & 1) * w_bytes), acc = tmem_base + (uint32_t)((j & 1) * kTile);
+                const uint32_t w0 = sW_addr + (uint32_t)((cn & 1) * w_bytes), acc = tmem_base + (uint32_t)((cn & 1) * kTile);
                 uint32_t accum = 0;
                 for (int kk = 0; kk < Ci / 16; ++kk) {
                     const uint32_t koff = kk * 2 * lbo;
@@ -979,21 +996,23 @@ __global__ void __launch_bounds__(256, 1) k_point_mlp1_multi(const Mlp1MultiPara
                         tc::mma_bf16(acc, a_lo, w_hi, idesc, 1);
                     }
                 }
-                tc::commit(&bar[j & 1]);
+                tc::commit(&bar[cn & 1]);
             }
-            if (j > 0) {   // the previous chunk's epilogue runs under this chunk's MMAs
-                if ((j - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+            if (j > 0) {   // the previous chunk's MMAs: once they are complete their weight buffer is free again
+                if ((cn - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
                 tc::fence_after_sync();
-                epilogue(j - 1);
             }
+            prefetch_w(j + 1 < p.n_chunks ? j + 1 : 0, (cn + 1) & 1);   // next chunk (of this tile, or the first one of the next tile)
+            if (j > 0) epilogue(j - 1, (cn - 1) & 1);   // runs under this chunk's MMAs and the weight prefetch
+            ++cn;
         }
         {
-            const int j = p.n_chunks - 1;
-            if (j & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+            if ((cn - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
             tc::fence_after_sync();
-            epilogue(j);
+            epilogue(p.n_chunks - 1, (cn - 1) & 1);
         }
     }
+    tc::cp_async_wait_all();
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_free(tmem_base, 256);
@@ -1273,7 +1292,7 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     // one CTA per SM (shared memory); an even share of tiles per CTA beats leaving a few CTAs with one tile more
     const int64_t waves = ceil_div64(tiles, sm_count());
     const int64_t grid = std::max<int64_t>(1, ceil_div64(tiles, waves));
-    kern<<<(unsigned)grid, 256, smem, st>>>(p);
+    kern<<<(unsigned)grid, 288, smem, st>>>(p);
     count_launches(1);
     return launch_status("cf_point_mlp1_multi (tcgen05)");
 }

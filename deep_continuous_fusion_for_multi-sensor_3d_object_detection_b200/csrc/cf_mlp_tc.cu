@@ -30,6 +30,9 @@
 // Weights are pre-packed once per call (k_pack_weights) into the shared-memory operand image, chunked along K;
 // up to C = 128 both layers stay resident in shared memory for the life of the CTA, above that chunks of 64 input
 // channels are streamed from L2 per use.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "cf_common.cuh"
 #include "cf_tcgen05.cuh"
 
@@ -1120,12 +1123,22 @@ int launch_tc(const TcParams &p, cudaStream_t st)
                            "k_fusion_tc smem attribute"));
         attr_bytes = smem;
     }
-    // CTAs per SM: limited by shared memory, TMEM columns (512 per SM, never oversubscribed) and threads
+    // The kernel is persistent with a static tile -> CTA assignment, so every CTA of the grid should be resident at
+    // once: CTAs per SM = min over shared memory, registers, threads and TMEM columns (512 per SM, never oversubscribed:
+    // a CTA that cannot allocate would spin inside tcgen05.alloc).
+    static int regs_per_thread = 0;
+    if (!regs_per_thread) {
+        cudaFuncAttributes fa;
+        CF_TRY(cuda_status(cudaFuncGetAttributes(&fa, k_fusion_tc<C, NS>), "k_fusion_tc attributes"));
+        regs_per_thread = (fa.numRegs + 7) / 8 * 8;
+    }
     const int by_smem = (227 * 1024) / (smem + 1024);
+    const int by_regs = 65536 / (regs_per_thread * NT);
     const int by_tmem = 512 / L::kTmemCols;  // 2 * C columns per CTA, rounded up to a power of two
-    const int by_threads = 2048 / NT;
-    const int per_sm = std::max(1, std::min(std::min(by_smem, by_tmem), std::min(by_threads, 8)));
+    const int by_occ = std::min(std::min(by_smem, by_regs), 2048 / NT);
+    const int per_sm = std::max(1, std::min(std::min(by_occ, by_tmem), 8));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
+    if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_tc<%d,%d>: occ %d tmem %d grid %lld smem %d\n", C, NS, by_occ, by_tmem, (long long)grid, smem);
     k_fusion_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }

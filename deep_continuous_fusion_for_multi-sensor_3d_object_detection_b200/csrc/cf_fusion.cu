@@ -54,7 +54,8 @@ extern "C" int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && H > 0 && W > 0 && Ci >= 0, CF_ERR_ARG, "cf_fusion_fwd: bad extents");
     CF_REQUIRE(C >= 16 && C <= 256 && C % 16 == 0, CF_ERR_ARG, "cf_fusion_fwd: C=%d must be a multiple of 16 in [16,256]", C);
     CF_REQUIRE(K >= 1 && K <= CF_MAX_K, CF_ERR_ARG, "cf_fusion_fwd: K=%d outside [1,%d]", K, CF_MAX_K);
-    CF_REQUIRE(aligned16(d_T) && aligned16(d_workspace), CF_ERR_ALIGN, "cf_fusion_fwd: T/workspace must be 16-byte aligned");
+    CF_REQUIRE((reinterpret_cast<uintptr_t>(d_T) & 31u) == 0 && aligned16(d_workspace), CF_ERR_ALIGN,
+               "cf_fusion_fwd: T must be 32-byte aligned, the workspace 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     switch (mode) {
         case CF_MODE_FP32_SIMT:

@@ -97,7 +97,7 @@ constexpr int kCopyBatch = CF_COPY_BATCH;  // channels per copy unit and thread 
 // the "row" a cell without a k-th neighbour gathers: relu(-1e30 - e) = 0, so the operand build needs no select
 #define CF_NEG8 -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f
 #define CF_NEG64 CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8, CF_NEG8
-__device__ float g_neg_row[256] = {CF_NEG64, CF_NEG64, CF_NEG64, CF_NEG64};
+__device__ __align__(32) float g_neg_row[256] = {CF_NEG64, CF_NEG64, CF_NEG64, CF_NEG64};
 #undef CF_NEG64
 #undef CF_NEG8
 
@@ -387,9 +387,8 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     // rows without a k-th neighbour read a row of -1e30, which the fused ReLU turns into zeros.
     auto gather = [&](const float *Tc, const float *neg, uint32_t idx_addr, float *t) {   // t[8]
         const int32_t pr = (int32_t)tc::lds_u32(idx_addr);
-        const float4 *trow = reinterpret_cast<const float4 *>(pr >= 0 ? Tc + (size_t)pr * C : neg);
-        const float4 a = __ldg(trow), c = __ldg(trow + 1);
-        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = c.x; t[5] = c.y; t[6] = c.z; t[7] = c.w;
+        // one 256-bit load per lane: the 4 lanes of a row fetch one full 128-byte line in a single request
+        tc::ldg_nc_f32x8(pr >= 0 ? Tc + (size_t)pr * C : neg, t);
     };
     auto build = [&](const float *t, const float4 &ctr, uint32_t dst_addr) {
         const float2 cxx = make_float2(ctr.x, ctr.y), cyy = make_float2(ctr.z, ctr.w);
@@ -1136,7 +1135,8 @@ int launch_tc(const TcParams &p, cudaStream_t st)
     const int by_regs = 65536 / (regs_per_thread * NT);
     const int by_tmem = 512 / L::kTmemCols;  // 2 * C columns per CTA, rounded up to a power of two
     const int by_occ = std::min(std::min(by_smem, by_regs), 2048 / NT);
-    const int per_sm = std::max(1, std::min(std::min(by_occ, by_tmem), 8));
+    int per_sm = std::max(1, std::min(std::min(by_occ, by_tmem), 8));
+    if (const char *cap = getenv("CF_MAX_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // tuning aid
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
     if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_tc<%d,%d>: occ %d tmem %d grid %lld smem %d\n", C, NS, by_occ, by_tmem, (long long)grid, smem);
     k_fusion_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);

@@ -217,6 +217,14 @@ __device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4 &hi, uin
 }
 
 
+// 256-bit read-only global load (sm_100: LDG.E.256), 32-byte aligned
+__device__ __forceinline__ void ldg_nc_f32x8(const float *p, float *v)
+{
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+        : "l"(p));
+}
+
 // ---- explicit shared-state-space accesses (32-bit addresses: no generic-pointer conversion in the inner loops) -----
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {

@@ -133,7 +133,7 @@ CF_API int cf_fusion_pack_weights(const float *d_W2, const float *d_W3, int32_t 
  * K-4  per-neighbour MLP layers 1b/2/3 + K-sum-pool + BEV add for one scale (Appendix A9, A10);
  * the result replaces `x` after a residual group in ResnetCustomed.forward (model.py:74-78).
  *   out[b,:,i,j] = bev[b,:,i,j] + W3 * sum_k relu(W2 relu(T[b,idx_k,:] - e_ij) + b2) + n_valid*b3
- *   d_bev/d_out (B,C,H,W) fp32 NCHW contiguous (may alias); C % 16 == 0, 16 <= C <= 256.
+ *   d_bev/d_out (B,C,H,W) fp32 NCHW contiguous (may alias: in place); C % 16 == 0, 16 <= C <= 256; d_T 32-byte aligned.
  *   mode: CF_MODE_*.   d_workspace: cf_fusion_workspace_bytes(C, mode, B, H, W) bytes (packed weights and the
  *   compacted list of cells that have a neighbour).  B <= 64 frames per call.
  * ------------------------------------------------------------------------------------------- */

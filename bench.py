@@ -56,6 +56,17 @@ def fusion_kernel_bytes(sc, B, K, live_frac=1.0):
     return float(B * cells * (2 * 4 * C + 4 + live_frac * 4 * K) + 4 * (2 * C * C + 4 * C))
 
 
+def recorded_traffic(workload, mode, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f).get(f"{workload}/{mode}/{kernel}")
+        return (float(e["dram_bytes_per_launch"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -373,8 +384,9 @@ def run_gpu(args):
         sc = [s for s in wl["scales"] if s["group"] == g][0]
         nbytes = fusion_kernel_bytes(sc, B, K, pipe.live_frac[g])
         ach = nbytes / (per_op[dom] * 1e-3) / 1e9
+        traffic, traffic_src = recorded_traffic(args.workload, mode, dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_launch": nbytes, "ms_per_launch": round(per_op[dom], 4),
                 "share_of_step": round(per_op[dom] / sum(per_op.values()), 3),
                 "cells_with_neighbour": round(pipe.live_frac[g], 4)}

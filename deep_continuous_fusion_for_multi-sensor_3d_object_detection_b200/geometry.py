@@ -59,6 +59,22 @@ def voxel_scales(config: dict):
     return x_scale, y_scale, x_offset, y_offset
 
 
+def voxel_matrix(config: dict):
+    """(x_scale, y_scale, z_scale, x_off, y_off, z_off) of pc_to_voxel_indice, data_import_carla.py:35-43 (Python-float
+    arithmetic, truncated to int exactly as the reference does)."""
+    xs, ys, xo, yo = voxel_scales(config)
+    zs = int(config["voxel_channel"] / (config["lidar_z_max"] - config["lidar_z_min"]))
+    return xs, ys, zs, xo, yo, int(-config["lidar_z_min"] * zs)
+
+
+def lidar_range(config: dict):
+    """(x_lo, x_hi, y_lo, y_hi, z_lo, z_hi) float32 thresholds of the range filter, data_import_carla.py:214-226:
+    keep lo < v < hi with hi = max - delta evaluated in double and then compared in float32."""
+    d = config["delta"]
+    return tuple(float(np.float32(v)) for v in (config["lidar_x_min"], config["lidar_x_max"] - d, config["lidar_y_min"],
+                                                config["lidar_y_max"] - d, config["lidar_z_min"], config["lidar_z_max"] - d))
+
+
 def scale_geometry(config: dict, stride: int):
     """BEV cell centres at a backbone scale.
 

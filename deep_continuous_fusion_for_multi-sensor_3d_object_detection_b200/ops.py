@@ -70,6 +70,39 @@ def bucket_points(points: torch.Tensor, num_points: torch.Tensor, grid: BucketGr
     return start, srt, ws
 
 
+def voxelize_project(raw, num_raw, config, calib, max_num_pc=None, workspace=None):
+    """Dataset side on the device: CarlaDataset.Voxelization_Projection (data_import_carla.py:212-267) for a batch.
+
+    raw (B,Nraw,3) f32 LiDAR xyz, num_raw (B,) valid rows -> (lidar_voxel (B,Z,X,Y), pointcloud_raw (B,max_num_pc,3),
+    projected_loc_uv (B,max_num_pc,2), num_points_raw (B,) int64): the sample[...] tensors of the reference dataset."""
+    import ctypes as C
+    from . import geometry as G
+    lib = load()
+    raw = _contig(raw, "raw", torch.float32, 3)
+    B, Nraw, three = raw.shape
+    if three != 3:
+        raise ValueError(f"raw: last dim must be 3, got {three}")
+    num_raw = as_counts(num_raw, B, raw.device)
+    Z, X, Y = int(config["voxel_channel"]), int(config["voxel_length"]), int(config["voxel_width"])
+    N = int(config["max_num_pc"] if max_num_pc is None else max_num_pc)
+    f6 = lambda v: (C.c_float * 6)(*[float(x) for x in v])
+    crt = np.ascontiguousarray(np.asarray(calib.detach().cpu() if isinstance(calib, torch.Tensor) else calib, dtype=np.float32))
+    if crt.shape != (4, 3):
+        raise ValueError(f"calib: expected CRT_tensor (4,3), got {crt.shape}")
+    need = lib.cf_voxelize_workspace_bytes(B, Nraw, Z, X, Y)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=raw.device)
+    vox = torch.empty((B, Z, X, Y), dtype=torch.float32, device=raw.device)
+    pts = torch.empty((B, N, 3), dtype=torch.float32, device=raw.device)
+    uv = torch.empty((B, N, 2), dtype=torch.float32, device=raw.device)
+    num = torch.empty((B,), dtype=torch.int64, device=raw.device)
+    check(lib.cf_voxelize_project(ptr(raw), ptr(num_raw), B, Nraw, f6(G.lidar_range(config)), f6(G.voxel_matrix(config)), Z, X, Y,
+                                  (C.c_float * 12)(*crt.ravel().tolist()), float(config["image_height"]),
+                                  float(config["image_width"]), N, ptr(vox), ptr(pts), ptr(uv), ptr(num), ptr(workspace),
+                                  stream_ptr()), "cf_voxelize_project")
+    return vox, pts, uv, num
+
+
 def knn_query(bucket_start, sorted_pts, grid: BucketGrid, H, W, geom, radius, K, out=None):
     """K-2.  -> knn_idx (B,H,W,K) int32, -1 = empty slot."""
     lib = load()

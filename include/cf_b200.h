@@ -166,6 +166,25 @@ CF_API int cf_point_gather_bwd(const float *d_gfeat, float *d_gimg, int64_t sb, 
                         float img_w, float img_h, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Dataset side on the device: CarlaDataset.Voxelization_Projection + .Projection,
+ * data_import_carla.py:196-267, for a batch of raw sweeps.  Produces every tensor the model consumes:
+ *   d_raw (B,Nraw,3) fp32 LiDAR xyz, d_num_raw (B) int64 valid rows per frame
+ *   h_range  6 HOST floats (x_lo, x_hi, y_lo, y_hi, z_lo, z_hi): keep lo < v < hi   (:214-226; hi = max - delta)
+ *   h_vox    6 HOST floats (x_scale, y_scale, z_scale, x_off, y_off, z_off) of pc_to_voxel_indice (:35-43)
+ *   h_calib  12 HOST floats = CRT_tensor (4,3);  0 < u < u_hi (image_height) and 0 < v < v_hi (image_width) [sic :202-205]
+ *   d_voxel  (B,Z,X,Y) fp32 out = sample["pointcloud"]: trilinear splat; of the points that share a voxel inside one of
+ *            the 8 `voxel[idx] += w` statements only the LAST counts (index_put_ without accumulation, :249-256)
+ *   d_points (B,max_num_pc,3), d_uv (B,max_num_pc,2) fp32 out, zero padded; d_num_points (B) int64 out
+ *            = sample["pointcloud_raw"], ["projected_loc_uv"], ["num_points_raw"] (:261-267); input order is kept
+ *   d_workspace cf_voxelize_workspace_bytes(...) bytes.  B <= 64, lidar_x_min >= 0.
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_voxelize_workspace_bytes(int32_t B, int32_t Nraw, int32_t Z, int32_t X, int32_t Y);
+CF_API int cf_voxelize_project(const float *d_raw, const int64_t *d_num_raw, int32_t B, int32_t Nraw,
+                        const float *h_range, const float *h_vox, int32_t Z, int32_t X, int32_t Y,
+                        const float *h_calib, float u_hi, float v_hi, int32_t max_num_pc, float *d_voxel,
+                        float *d_points, float *d_uv, int64_t *d_num_points, void *d_workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * P-1  Test.get_bboxes (test.py:88-108) on device: per frame, anchor 0 then anchor 1, cells in
  * row-major order with cls[b,2a+1] > thr; gathers the 7 decoded channels [7a,7a+7).
  *   d_pred_cls (B,4,H,W), d_pred_box (B,14,H,W) fp32; d_boxes (B,cap,7) out; d_counts (B) int32 out

@@ -132,6 +132,21 @@ def main():
                         crt=ds.CRT_tensor.numpy())
     print("projection", raw.shape[0], "->", num)
 
+    # ---- voxelisation + projection (data_import_carla.py:212-267), the reference's own tensors on two sweeps.
+    # `voxel[idx] += w` with repeated indices is an index_put_ without accumulation: on several threads the winner among
+    # the points that share a voxel depends on torch's intra-op scheduling (8 threads here: ~0.3 % of the nonzero voxels
+    # differ from run to run / from the sequential result).  The fixture pins the SEQUENTIAL semantics (last point wins).
+    torch.set_num_threads(1)
+    for tag, seed, beams, az in (("a", 17, 32, 700), ("b", 18, 64, 400)):
+        raw = dcf_b200.synthetic.lidar_sweep(np.random.default_rng(seed), beams, az)
+        vox, pc, uv, num, _ = ds.Voxelization_Projection(torch.from_numpy(raw))
+        vox = vox.numpy()
+        nzi = np.flatnonzero(vox).astype(np.int32)
+        np.savez_compressed(os.path.join(OUT, f"voxelize_{tag}.npz"), raw=raw, vox_shape=np.array(vox.shape),
+                            vox_idx=nzi, vox_val=vox.ravel()[nzi], pointcloud_raw=pc.numpy()[:num + 8],
+                            projected_loc_uv=uv.numpy()[:num + 8], num_points_raw=np.int64(num), crt=ds.CRT_tensor.numpy())
+        print("voxelize", tag, raw.shape[0], "->", num, "nonzero voxels", nzi.size)
+
 
 if __name__ == "__main__":
     main()

@@ -248,3 +248,68 @@ def get_bboxes(cls4, box14, thr=0.8):
     out = np.empty((2 * H * W, 7), dtype=np.float32)
     n = lib().cfo_get_bboxes(_p(cls4, _f32p), _p(box14, _f32p), H, W, np.float32(thr), _p(out, _f32p))
     return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Dataset-side voxelisation + projection: numpy restatement of CarlaDataset.Voxelization_Projection
+# and .Projection, data_import_carla.py:196-267, statement by statement.  Pinned against the reference's own code
+# run on synthetic sweeps (tests/golden/voxelize.npz, oracle/gen_golden.py).
+# ---------------------------------------------------------------------------------------------------------------
+def voxel_matrix(config):
+    """pc_to_voxel_indice, data_import_carla.py:35-43: integer scales / offsets computed with Python floats."""
+    xs = int(config["voxel_length"] / (config["lidar_x_max"] - config["lidar_x_min"]))
+    ys = int(config["voxel_width"] / (config["lidar_y_max"] - config["lidar_y_min"]))
+    zs = int(config["voxel_channel"] / (config["lidar_z_max"] - config["lidar_z_min"]))
+    return (xs, ys, zs, int(-config["lidar_x_min"] * xs), int(-config["lidar_y_min"] * ys), int(-config["lidar_z_min"] * zs))
+
+
+def voxelize_project(raw, config, crt):
+    """raw (n,3) float32 -> (lidar_voxel (Z,X,Y) f32, pointcloud_raw (max_num_pc,3), uv (max_num_pc,2), num).
+
+    Follows the reference line by line, including its quirks:
+      * the range filter zeroes rejected points and keeps the first count_nonzero/3 columns of nonzero() (:214-229);
+      * the trilinear splat uses `voxel[idx] += w` with advanced indexing, i.e. for points that fall into the same
+        voxel within one of the 8 statements only the LAST one counts (:236-258);
+      * the image filter compares u with image_height and v with image_width (:202-205) and has the same
+        nonzero()/2 rule (:206-207)."""
+    f32 = np.float32
+    raw = np.ascontiguousarray(raw, dtype=f32)
+    x, y, z = raw[:, 0], raw[:, 1], raw[:, 2]
+    d = config["delta"]
+    # the thresholds are Python floats (max - delta in double), promoted to float32 by the tensor comparison
+    keep = ((x > f32(config["lidar_x_min"])) & (x < f32(config["lidar_x_max"] - d)) & (y > f32(config["lidar_y_min"])) &
+            (y < f32(config["lidar_y_max"] - d)) & (z > f32(config["lidar_z_min"])) & (z < f32(config["lidar_z_max"] - d)))
+    surv = np.nonzero(keep)[0]
+    nz = int((raw[surv] != 0).sum())
+    rows = np.nonzero((raw[surv] != 0).T)          # nonzero() of the (3, N) tensor: row-major order
+    cols = rows[1][: nz // 3]                        # first third of the entries = column indices
+    pts = raw[surv][cols]
+    xs, ys, zs, xo, yo, zo = voxel_matrix(config)
+    fx = pts[:, 0] * f32(xs) + f32(xo)
+    fy = pts[:, 1] * f32(ys) + f32(yo)
+    fz = pts[:, 2] * f32(zs) + f32(zo)
+    xl, yl, zl = fx.astype(np.int64), fy.astype(np.int64), fz.astype(np.int64)
+    dx, dy, dz = fx - xl.astype(f32), fy - yl.astype(f32), fz - zl.astype(f32)
+    one = f32(1)
+    vox = np.zeros((config["voxel_channel"], config["voxel_length"], config["voxel_width"]), dtype=f32)
+    for zi, xi, yi, w in ((zl, xl, yl, (one - dx) * (one - dy) * (one - dz)), (zl + 1, xl, yl, (one - dx) * (one - dy) * dz),
+                          (zl, xl + 1, yl, dx * (one - dy) * (one - dz)), (zl + 1, xl + 1, yl, dx * (one - dy) * dz),
+                          (zl, xl, yl + 1, (one - dx) * dy * (one - dz)), (zl + 1, xl, yl + 1, (one - dx) * dy * dz),
+                          (zl, xl + 1, yl + 1, dx * dy * (one - dz)), (zl + 1, xl + 1, yl + 1, dx * dy * dz)):
+        vox[zi, xi, yi] += w                         # numpy fancy `+=`: last write wins, like torch index_put_
+    # Projection
+    crt = np.asarray(crt, dtype=f32)
+    q = (pts[:, 0:1] * crt[0] + pts[:, 1:2] * crt[1]) + (pts[:, 2:3] * crt[2] + crt[3])
+    u, v = q[:, 0] / q[:, 2], q[:, 1] / q[:, 2]
+    ok = (u > 0) & (u < f32(config["image_height"])) & (v > 0) & (v < f32(config["image_width"]))
+    s2 = np.nonzero(ok)[0]
+    uv2 = np.stack([u[s2], v[s2]], axis=0)
+    r2 = np.nonzero(uv2 != 0)
+    c2 = r2[1][: int((uv2 != 0).sum()) // 2]
+    num = c2.shape[0]
+    N = int(config["max_num_pc"])
+    pc = np.zeros((N, 3), dtype=f32)
+    uvp = np.zeros((N, 2), dtype=f32)
+    pc[:num] = pts[s2][c2]
+    uvp[:num] = uv2.T[c2]
+    return vox, pc, uvp, num

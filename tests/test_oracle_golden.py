@@ -93,3 +93,21 @@ def test_projection_and_filter(oracle, golden, dcf):
     # oracle projection (Appendix A6) agrees with the dataset's precomputed uv to 1e-3 px
     uv_o = oracle.project_points(p, g["crt"])
     assert np.abs(uv_o - g["projected_loc_uv"][:n]).max() < 2e-3
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_voxelize_project_restatement_matches_reference(oracle, golden, dcf, tag):
+    """oracle.voxelize_project restates CarlaDataset.Voxelization_Projection (data_import_carla.py:212-267); the
+    fixture holds the reference's own tensors (sequential index_put_ semantics, see oracle/gen_golden.py)."""
+    g = golden(f"voxelize_{tag}.npz")
+    cfg = dcf.geometry.carla_config()
+    vox, pc, uv, num = oracle.voxelize_project(g["raw"], cfg, g["crt"])
+    ref = np.zeros(int(np.prod(g["vox_shape"])), np.float32)
+    ref[g["vox_idx"]] = g["vox_val"]
+    n = int(g["num_points_raw"])
+    assert num == n
+    assert np.array_equal(vox.ravel(), ref)                                   # voxel grid: bit-exact
+    assert np.array_equal(pc[:n + 8], g["pointcloud_raw"])                    # points: exact, zero padded
+    assert np.abs(uv[:n + 8] - g["projected_loc_uv"]).max() < 2e-3            # BLAS vs explicit summation order
+    # host helpers reproduce pc_to_voxel_indice and the float32 thresholds
+    assert dcf.geometry.voxel_matrix(cfg) == oracle.voxel_matrix(cfg) == (5, 4, 10, 0, 120, 24)

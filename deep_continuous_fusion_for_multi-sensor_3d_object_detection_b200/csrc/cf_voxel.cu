@@ -3,7 +3,8 @@
 //   range filter -> trilinear splat into the (Z, X, Y) voxel grid -> camera projection + image filter -> zero-padded
 //   pointcloud_raw / projected_loc_uv / num_points_raw, i.e. every tensor the LiDAR backbone and the fusion layer consume.
 //
-// Semantics follow the reference statement by statement (oracle: oracle.voxelize_project, pinned against the reference):
+// Semantics follow the reference statement by statement (the CPU restatement in the test infrastructure is pinned against
+// the reference's own tensors):
 //   * survivors keep their input order (ordered block-scan compaction, one CTA per frame);
 //   * `voxel[idx] += w` with advanced indexing is an index_put_ WITHOUT accumulation: within each of the 8 splat statements,
 //     of the points that fall into the same voxel only the LAST one counts.  Reproduced deterministically with an owner

@@ -288,10 +288,11 @@ extern "C" int cf_point_mlp1_multi(const float *d_feat, const float *d_points, c
                "cf_point_mlp1_multi: null pointer");
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && Ci > 0 && n_scales > 0, CF_ERR_ARG, "cf_point_mlp1_multi: bad extents");
     CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_point_mlp1_multi: mode %d has no tensor-core path", mode);
-    CF_REQUIRE(aligned16(d_feat), CF_ERR_ALIGN, "cf_point_mlp1_multi: feat must be 16-byte aligned");
+    CF_REQUIRE((reinterpret_cast<uintptr_t>(d_feat) & 31u) == 0, CF_ERR_ALIGN, "cf_point_mlp1_multi: feat must be 32-byte aligned");
     for (int s = 0; s < n_scales && s < 64; ++s) {
         CF_REQUIRE(h_W1[s] && h_b1[s] && h_T[s] && h_packed[s], CF_ERR_ARG, "cf_point_mlp1_multi: null pointer for scale %d", s);
-        CF_REQUIRE(aligned16(h_T[s]) && aligned16(h_packed[s]), CF_ERR_ALIGN, "cf_point_mlp1_multi: T / packed weights of scale %d must be 16-byte aligned", s);
+        CF_REQUIRE((reinterpret_cast<uintptr_t>(h_T[s]) & 31u) == 0 && aligned16(h_packed[s]), CF_ERR_ALIGN,
+                   "cf_point_mlp1_multi: T of scale %d must be 32-byte aligned, its packed weights 16-byte aligned", s);
     }
     const int rc = point_mlp1_multi_tc(d_feat, d_points, d_num_points, B, N, Ci, n_scales, h_C, h_W1, h_b1, h_T, mode,
                                        h_packed, (cudaStream_t)stream);

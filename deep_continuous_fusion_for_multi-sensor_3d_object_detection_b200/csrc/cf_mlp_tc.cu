@@ -833,6 +833,7 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
 // previous chunk (rank-3 offset + bias, write T) runs under them.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxScales = 8, kMaxChunks = 16;
+constexpr int kMultiThreads = 544;   // 16 worker warps + the MMA issuer warp
 struct Mlp1MultiParams {
     const float *feat;
     const float *points;
@@ -847,11 +848,11 @@ struct Mlp1MultiParams {
 };
 
 template <int NS>
-__global__ void __launch_bounds__(288, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
+__global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
 {
-    // warps 0-7: workers (operand build, weight prefetch, epilogues); warp 8: its lane 0 only issues the MMAs, so the
-    // ~70 tcgen05.mma of a chunk never sit in front of a worker warp's epilogue
-    constexpr int NT = 256, NW = NT / 32, kIssuer = 256;
+    // warps 0-15: workers (operand build, weight prefetch, epilogues; 4 threads per row split the columns of a chunk);
+    // warp 16: its lane 0 only issues the MMAs, so the ~70 tcgen05.mma of a chunk never sit in front of an epilogue
+    constexpr int NT = kMultiThreads - 32, NW = NT / 32, kIssuer = NT, kColGroups = NT / kTile;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar[2];
     __shared__ uint32_t tmem_slot;
@@ -911,21 +912,18 @@ __global__ void __launch_bounds__(288, 1) k_point_mlp1_multi(const Mlp1MultiPara
         // the loads of a batch of items are all issued before the first one is split and stored ------------------------
         const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
         const int n_items = 16 * (kc_units / 4);
-        constexpr int kBatch = 8;
+        constexpr int kBatch = 4;
         for (int item0 = warp; worker && item0 < n_items; item0 += NW * kBatch) {
-            float4 t0[kBatch], t1[kBatch];
+            float t[kBatch][8];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int item = item0 + u * NW;
                 const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
                 const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
-                t0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                t1[u] = t0[u];
-                if (item < n_items && m0 + r < n_pts) {
-                    const float4 *src = reinterpret_cast<const float4 *>(fb + (size_t)r * Ci + ku * 8);
-                    t0[u] = __ldg(src);
-                    t1[u] = __ldg(src + 1);
-                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[u][i] = 0.0f;
+                // one 256-bit load per lane: the 4 lanes of a row fetch one full 128-byte line per request
+                if (item < n_items && m0 + r < n_pts) tc::ldg_nc_f32x8(fb + (size_t)r * Ci + ku * 8, t[u]);
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
@@ -933,9 +931,8 @@ __global__ void __launch_bounds__(288, 1) k_point_mlp1_multi(const Mlp1MultiPara
                 if (item < n_items) {
                     const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
                     const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
-                    const float v[8] = {t0[u].x, t0[u].y, t0[u].z, t0[u].w, t1[u].x, t1[u].y, t1[u].z, t1[u].w};
                     uint4 hi, lo;
-                    tc::split_bf16x8(v, hi, lo, NS == 2);
+                    tc::split_bf16x8(t[u], hi, lo, NS == 2);
                     const uint32_t off = tc::unit_offset(r, ku, kc_units);
                     *reinterpret_cast<uint4 *>(sA + off) = hi;
                     if (NS == 2) *reinterpret_cast<uint4 *>(sA + kTile * Ci * 2 + off) = lo;
@@ -956,20 +953,19 @@ __global__ void __launch_bounds__(288, 1) k_point_mlp1_multi(const Mlp1MultiPara
             const uint32_t acc = tmem_base + buf * kTile + lane_off;
             float *trow = p.T[s] + ((size_t)b * p.N + m) * C + n0;
 #pragma unroll 1
-            for (int c = half * 16; worker && c < len; c += 32) {
+            for (int c = half * 16; worker && c < len; c += 16 * kColGroups) {
                 float z[16];
                 tc::tmem_ld16(acc + c, z);
                 if (live) {
-                    float4 *dst = reinterpret_cast<float4 *>(trow + c);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        float o[4];
+                    for (int q8 = 0; q8 < 2; ++q8) {   // 256-bit stores: every lane writes full 32-byte sectors of its row
+                        float o[8];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 w = f[n0 + c + q4 * 4 + i];
-                            o[i] = z[q4 * 4 + i] + (w.y * px + w.z * py + w.w * pz) + w.x;
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 w = f[n0 + c + q8 * 8 + i];
+                            o[i] = z[q8 * 8 + i] + (w.y * px + w.z * py + w.w * pz) + w.x;
                         }
-                        dst[q4] = make_float4(o[0], o[1], o[2], o[3]);
+                        tc::stg_f32x8(trow + c + q8 * 8, o);
                     }
                 }
             }
@@ -1305,7 +1301,7 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     // one CTA per SM (shared memory); an even share of tiles per CTA beats leaving a few CTAs with one tile more
     const int64_t waves = ceil_div64(tiles, sm_count());
     const int64_t grid = std::max<int64_t>(1, ceil_div64(tiles, waves));
-    kern<<<(unsigned)grid, 288, smem, st>>>(p);
+    kern<<<(unsigned)grid, kMultiThreads, smem, st>>>(p);
     count_launches(1);
     return launch_status("cf_point_mlp1_multi (tcgen05)");
 }

@@ -225,6 +225,14 @@ __device__ __forceinline__ void ldg_nc_f32x8(const float *p, float *v)
         : "l"(p));
 }
 
+// 256-bit global store (sm_100: STG.E.256): a full 32-byte sector per lane, 32-byte aligned
+__device__ __forceinline__ void stg_f32x8(float *p, const float *v)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 // ---- explicit shared-state-space accesses (32-bit addresses: no generic-pointer conversion in the inner loops) -----
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {

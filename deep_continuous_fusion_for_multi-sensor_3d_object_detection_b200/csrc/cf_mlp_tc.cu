@@ -678,6 +678,403 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_fusion_sk: the fused kernel for C <= 128 with the MMAs taken off the tile's critical path.  Same tiles, same operand
+// build, same epilogues and the same arithmetic as k_fusion_tc (bit-identical results), but two A buffers, two bias
+// operands, two TMEM accumulators and two mbarriers: round k+1 is built and issued while the MMAs of round k run, and the
+// epilogue of round k runs under the MMAs of round k+1:
+//     prologue   build(0) | sync | issue(0) | gather(1)
+//     round k    build(k+1) | sync | issue(k+1) | gather(k+2) | wait(k) | epilogue(k)
+//     layer 3    pooled -> A | sync | issue | wait | out = bev + acc
+// To keep the occupancy of k_fusion_tc with the second A buffer, W3 is not resident: it streams (cp.async) into the A
+// buffer that the last round does not use, during the last-but-one round's epilogue.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int NS>
+struct SkLayout {
+    static constexpr int kWBytes = NS * C * C * 2;                  // one layer's packed image (W2 resident; W3 streamed)
+    static constexpr int kABytes = NS * kTile * C * 2;              // one A tile (all splits)
+    static_assert(kWBytes <= kABytes, "W3 is staged in an A buffer");
+    static constexpr int kOffA = kWBytes;                           // A[2]
+    static constexpr int kAbBytes = kTile * 32;
+    static constexpr int kOffAb = kOffA + 2 * kABytes;              // Ab[2]
+    static constexpr int kWbBytes = C * 32;
+    static constexpr int kOffWb = kOffAb + 2 * kAbBytes;            // bias B operands of layer 2 | layer 3
+    static constexpr int kOffCtr = kOffWb + 2 * kWbBytes;           // float2 (cx, cy) [2][128]
+    static constexpr int kOffCell = kOffCtr + 2 * kTile * 8;        // int32 [2][128]
+    static constexpr int kOffW1 = kOffCell + 2 * kTile * 4;         // negated offset weights
+    static constexpr int kOffBar = kOffW1 + 2 * C * 4;              // mbarrier[2] (16 B), tmem ptr (4 B), pad, int wmax[2][4]
+    static constexpr int kOffIdx = kOffBar + 64;                    // int32 [2][K][128]
+    static __host__ __device__ constexpr int smem_bytes(int K) { return kOffIdx + 2 * K * kTile * 4; }
+    static constexpr int kTmemCols = tmem_cols_for(3 * C);          // two accumulators + the pooled sum
+};
+
+template <int C, int NS>
+__global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks) k_fusion_sk(const TcParams p)
+{
+    using L = SkLayout<C, NS>;
+    constexpr int G = TcShape<C>::G, EW = kEW;
+    constexpr int NT = kTile * G, NW = NT / 32;
+    constexpr int kc_units = C / 8, kQuads = kc_units / 4, kStep = NW / kQuads;
+    constexpr int kChunksE = C / EW;
+    static_assert(NW % kQuads == 0 && 16 % kStep == 0 && 16 / kStep == 4, "4 operand items per warp and round");
+    static_assert(C % G == 0 && (C / G) % 32 == 0, "column split between the thread groups");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sW = smem;
+    uint8_t *sAb = smem + L::kOffAb;
+    uint8_t *sWb = smem + L::kOffWb;
+    float2 *sctr = reinterpret_cast<float2 *>(smem + L::kOffCtr);
+    int32_t *scell = reinterpret_cast<int32_t *>(smem + L::kOffCell);
+    float *swn = reinterpret_cast<float *>(smem + L::kOffW1);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 16);
+    int32_t *swmax = reinterpret_cast<int32_t *>(smem + L::kOffBar + 32);     // [2][4]
+    int32_t *sidx = reinterpret_cast<int32_t *>(smem + L::kOffIdx);           // [2][K][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (kTile - 1), grp = tid / kTile;
+    const int K = p.K;
+    const int64_t cells = (int64_t)p.H * p.W;
+
+    // ---- one-time setup -----------------------------------------------------------------------------------------
+    if (tid == 0) {
+        tc::mbar_init(&bar[0], 1);
+        tc::mbar_init(&bar[1], 1);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(tmem_slot, L::kTmemCols);
+    for (int c = tid; c < C; c += NT) {
+        swn[(c >> 3) * 16 + (c & 7)] = -__ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci);
+        swn[(c >> 3) * 16 + 8 + (c & 7)] = -__ldg(p.W1 + (size_t)c * (p.Ci + 3) + p.Ci + 1);
+    }
+    for (int o = tid * 16; o < 2 * L::kAbBytes + 2 * L::kWbBytes; o += NT * 16) *reinterpret_cast<uint4 *>(sAb + o) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int n = tid; n < 2 * C; n += NT) {
+        const int layer = n / C, c = n - layer * C;
+        const float bv = __ldg((layer ? p.b3 : p.b2) + c);
+        const __nv_bfloat16 h = __float2bfloat16_rn(bv);
+        const __nv_bfloat16 l = __float2bfloat16_rn(bv - __bfloat162float(h));
+        const uint32_t packed = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+        *reinterpret_cast<uint32_t *>(sWb + layer * L::kWbBytes + tc::unit_offset(c, 0, 2)) = packed;
+    }
+    copy_chunk<NT>(sW, p.wimg2, L::kWBytes);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_pool = tmem_base + 2 * C;                       // acc[a]: columns [a*C, (a+1)*C); pooled: [2C, 3C)
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t sW_addr = tc::smem_u32(sW), sA_addr = tc::smem_u32(smem + L::kOffA);
+    const uint32_t sAb_addr = tc::smem_u32(sAb), sWb_addr = tc::smem_u32(sWb);
+    const uint32_t sidx_addr = tc::smem_u32(sidx), sctr_addr = tc::smem_u32(sctr), swn_addr = tc::smem_u32(swn);
+    const uint32_t ab_row = sAb_addr + tc::unit_offset(row, 0, 2);
+    constexpr uint32_t idesc = tc::make_idesc_bf16(kTile, C);
+    uint32_t ph = 0, iter = 0;   // ph: bit a = phase of mbarrier a
+
+    const int ku = (warp % kQuads) * 4 + (lane >> 3);
+    const int r8 = lane & 7;
+    const int rg0 = warp / kQuads;
+    float2 nx[4], ny[4];
+    auto load_offset_weights = [&]() {
+        const uint32_t a = swn_addr + (uint32_t)(ku * 64);
+        const float4 x0 = tc::lds_f32x4(a), x1 = tc::lds_f32x4(a + 16), y0 = tc::lds_f32x4(a + 32), y1 = tc::lds_f32x4(a + 48);
+        nx[0] = make_float2(x0.x, x0.y); nx[1] = make_float2(x0.z, x0.w); nx[2] = make_float2(x1.x, x1.y); nx[3] = make_float2(x1.z, x1.w);
+        ny[0] = make_float2(y0.x, y0.y); ny[1] = make_float2(y0.z, y0.w); ny[2] = make_float2(y1.x, y1.y); ny[3] = make_float2(y1.z, y1.w);
+    };
+
+    const int32_t tpf = (int32_t)p.tiles_per_frame;
+    auto n_live_of = [&](int b) -> int32_t { return p.cell_list ? __ldg(p.cell_count + b) : (int32_t)cells; };
+    auto advance = [&](int32_t &b, int32_t &q, int32_t step) {
+        q += step;
+        while (q >= tpf) {
+            q -= tpf;
+            ++b;
+        }
+    };
+    auto seek_live = [&](int32_t &b, int32_t &q) {
+        while (b < p.B && q * kTile >= n_live_of(b)) advance(b, q, (int32_t)gridDim.x);
+    };
+    auto header_cell = [&](int32_t b, int32_t q) -> int32_t {
+        const int32_t e = q * kTile + row;
+        if (e >= n_live_of(b)) return -1;
+        return p.cell_list ? __ldg(p.cell_list + (size_t)b * cells + e) : e;
+    };
+    auto header_fill = [&](int32_t b, int32_t cell, int par) {
+        const uint32_t dst = sidx_addr + (uint32_t)((par * K * kTile + row) * 4);
+        float cx = 0.f, cy = 0.f;
+        if (cell >= 0) {
+            const int32_t *kr = p.knn + ((size_t)b * cells + cell) * K;
+            for (int k = 0; k < K; ++k) tc::cp_async4(dst + k * kTile * 4, kr + k);
+            const int32_t i = (int32_t)((uint32_t)cell / (uint32_t)p.W), j = cell - i * p.W;
+            cx = __fadd_rn(p.x0, __fmul_rn((float)i, p.dx));
+            cy = __fadd_rn(p.y0, __fmul_rn((float)j, p.dy));
+        } else {
+            for (int k = 0; k < K; ++k) tc::sts_u32(dst + k * kTile * 4, 0xFFFFFFFFu);
+        }
+        tc::cp_async_commit();
+        sctr[par * kTile + row] = make_float2(cx, cy);
+        scell[par * kTile + row] = cell;
+    };
+    auto wait_bar = [&](uint32_t a) {
+        tc::mbar_wait(&bar[a], (ph >> a) & 1u);
+        ph ^= 1u << a;
+        tc::fence_after_sync();
+    };
+
+    int32_t cb = 0, cq = 0, db = 0, dq = 0;   // cursors: MLP tiles (cb, cq), copy units (db, dq)
+    advance(cb, cq, (int32_t)blockIdx.x);
+    seek_live(cb, cq);
+    if (p.copy_dead) advance(db, dq, (int32_t)blockIdx.x); else db = p.B;
+    if (cb < p.B && grp == 0) header_fill(cb, header_cell(cb, cq), 0);
+
+    while (cb < p.B || db < p.B) {
+        if (cb < p.B) {
+            const int par = iter & 1;
+            ++iter;
+            const int b = cb;
+            int32_t nb = cb, nq = cq;
+            advance(nb, nq, (int32_t)gridDim.x);
+            seek_live(nb, nq);
+            const bool has_next = nb < p.B;
+            int n_valid = 0;
+            if (grp == 0) {
+                tc::cp_async_wait_all();
+                for (int k = 0; k < K; ++k) n_valid += (int32_t)tc::lds_u32(sidx_addr + (uint32_t)(((par * K + k) * kTile + row) * 4)) >= 0;
+                const int wm = __reduce_max_sync(0xffffffffu, n_valid);
+                if (lane == 0) swmax[par * 4 + warp] = wm;
+            }
+            __syncthreads();
+            int R;
+            {
+                const int4 wm = *reinterpret_cast<const int4 *>(swmax + par * 4);
+                R = max(max(wm.x, wm.y), max(wm.z, wm.w));
+            }
+            const int32_t cell = scell[par * kTile + row];
+            const bool in_range = cell >= 0;
+            int32_t ncell = -1;
+            if (grp == 0 && has_next) ncell = header_cell(nb, nq);
+
+            const float *Tc = p.T + (size_t)b * p.N * C + ku * 8, *neg = g_neg_row + ku * 8;
+            const uint32_t idx0 = sidx_addr + (uint32_t)((par * K * kTile + rg0 * 8 + r8) * 4);
+            const uint32_t ctr0 = sctr_addr + (uint32_t)((par * kTile + rg0 * 8 + r8) * 8);
+            const uint32_t dst0 = sA_addr + tc::unit_offset(r8, ku, kc_units) + (uint32_t)(rg0 * kc_units * 128);
+            const float *src_bev = p.bev + (size_t)b * C * cells + cell;
+            float tv[32];   // neighbour rows of the next round to build; in the last round: bev values of the final epilogue
+            auto gather_round = [&](int k) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int32_t pr = (int32_t)tc::lds_u32(idx0 + (uint32_t)(k * kTile * 4 + i * kStep * 32));
+                    tc::ldg_nc_f32x8(pr >= 0 ? Tc + (size_t)pr * C : neg, tv + 8 * i);
+                }
+            };
+            auto prefetch_bev = [&]() {
+                if (in_range) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (grp + j * G < kChunksE) {
+#pragma unroll
+                            for (int i = 0; i < EW; ++i) tv[j * EW + i] = __ldcs(src_bev + (size_t)((grp + j * G) * EW + i) * cells);
+                        }
+                    }
+                }
+            };
+            // A[buf] = relu(T[idx_k] - e) for the rows gathered in tv; bias flag of round k -> Ab[buf]
+            auto build_round = [&](int k, uint32_t buf) {
+                load_offset_weights();
+                const uint32_t dstb = dst0 + buf * L::kABytes;
+                float2 ctr = tc::lds_f32x2(ctr0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 ctr_next = ctr;
+                    if (i < 3) ctr_next = tc::lds_f32x2(ctr0 + (i + 1) * kStep * 64);
+                    const float2 cxx = make_float2(ctr.x, ctr.x), cyy = make_float2(ctr.y, ctr.y);
+                    float2 v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        v[e] = tc::ffma2(nx[e], cxx, tc::ffma2(ny[e], cyy, make_float2(tv[8 * i + 2 * e], tv[8 * i + 2 * e + 1])));
+                    uint4 hi, lo;
+                    tc::relu_split_bf16x8(v, hi, lo, NS == 2);
+                    const uint32_t d = dstb + i * kStep * kc_units * 128;
+                    tc::sts_u32x4(d, hi);
+                    if (NS == 2) tc::sts_u32x4(d + kTile * C * 2, lo);
+                    ctr = ctr_next;
+                }
+                if (grp == 0)
+                    tc::sts_u32(ab_row + buf * L::kAbBytes,
+                                (int32_t)tc::lds_u32(sidx_addr + (uint32_t)(((par * K + k) * kTile + row) * 4)) >= 0 ? 0x3F803F80u : 0u);
+            };
+            // acc[buf] = flag * b + A[buf] * W^T   (w_addr: the layer's packed image, wb: its bias operand)
+            auto issue_round = [&](uint32_t buf, uint32_t acc, uint32_t w_addr, uint32_t wb_addr) {
+                if (tid == 0) {
+                    tc::fence_after_sync();
+                    tc::mma_bf16(tmem_base + acc * C, tc::make_desc(sAb_addr + buf * L::kAbBytes, 128, 256),
+                                 tc::make_desc(wb_addr, 128, 256), idesc, 0u);
+                    issue_chunk<C, NS, C>(sA_addr + buf * L::kABytes, w_addr, tmem_base + acc * C, true);
+                    tc::commit(&bar[acc]);
+                }
+            };
+            auto stream_w3 = [&](uint32_t buf) {   // W3's packed image -> A[buf] (free: its last MMAs are complete)
+                const uint32_t dst = sA_addr + buf * L::kABytes;
+                for (int o = tid * 16; o < L::kWBytes; o += NT * 16) tc::cp_async16(dst + o, p.wimg3 + o);
+                tc::cp_async_commit();
+            };
+            auto epilogue_round = [&](int k, uint32_t acc) {   // pooled (+)= relu(acc)
+                __syncwarp();
+#pragma unroll 1
+                for (int cc = grp; cc < kChunksE; cc += G) {
+                    float z[EW], s[EW];
+                    if (k > 0) {
+                        tc::tmem_ld16x2(tmem_base + acc * C + lane_off + cc * EW, tmem_pool + lane_off + cc * EW, z, s);
+#pragma unroll
+                        for (int i = 0; i < EW; i += 2) {
+                            const float2 a = tc::fadd2(make_float2(s[i], s[i + 1]), make_float2(fmaxf(z[i], 0.f), fmaxf(z[i + 1], 0.f)));
+                            s[i] = a.x;
+                            s[i + 1] = a.y;
+                        }
+                    } else {
+                        tc::tmem_ld<EW>(tmem_base + acc * C + lane_off + cc * EW, z);
+#pragma unroll
+                        for (int i = 0; i < EW; ++i) s[i] = fmaxf(z[i], 0.f);
+                    }
+                    tc::tmem_st<EW>(tmem_pool + lane_off + cc * EW, s);
+                }
+                tc::fence_before_sync();
+            };
+
+            if (R == 0) {
+                if (grp == 0 && has_next) header_fill(nb, ncell, par ^ 1);
+                prefetch_bev();
+            } else {
+                // ---- prologue: round 0 -------------------------------------------------------------------------------------
+                gather_round(0);
+                build_round(0, 0);
+                tc::fence_proxy_async();
+                tc::fence_before_sync();
+                __syncthreads();
+                issue_round(0, 0, sW_addr, sWb_addr);
+                if (grp == 0 && has_next) header_fill(nb, ncell, par ^ 1);
+                if (R > 1) {
+                    gather_round(1);
+                } else {
+                    stream_w3(1);
+                    prefetch_bev();
+                }
+                for (int k = 0; k < R; ++k) {
+                    const uint32_t a = k & 1;
+                    if (k + 1 < R) {   // build and issue round k+1 while the MMAs of round k run
+                        build_round(k + 1, a ^ 1);
+                        tc::fence_proxy_async();
+                        tc::fence_before_sync();
+                        __syncthreads();
+                        issue_round(a ^ 1, a ^ 1, sW_addr, sWb_addr);
+                        if (k + 2 < R) gather_round(k + 2); else prefetch_bev();
+                    }
+                    wait_bar(a);
+                    if (k == R - 2) stream_w3(a);   // A[a] is free now; the last round uses A[a ^ 1]
+                    epilogue_round(k, a);
+                }
+                // ---- layer 3: acc = n_valid * b3 + pooled * W3^T  (pooled -> A[l]; W3 sits in A[l ^ 1]) --------------------
+                const uint32_t l = (R - 1) & 1;
+                __syncwarp();
+#pragma unroll 1
+                for (int cc = grp; cc < C / EW; cc += G) {
+                    float s[EW];
+                    tc::tmem_ld<EW>(tmem_pool + lane_off + cc * EW, s);
+#pragma unroll
+                    for (int q = 0; q < EW / 8; ++q) {
+                        float2 v[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = make_float2(s[q * 8 + 2 * i], s[q * 8 + 2 * i + 1]);
+                        uint4 hi, lo;
+                        tc::relu_split_bf16x8(v, hi, lo, NS == 2);   // pooled >= 0: the ReLU is the identity here
+                        const uint32_t off = sA_addr + l * L::kABytes + tc::unit_offset(row, cc * (EW / 8) + q, kc_units);
+                        tc::sts_u32x4(off, hi);
+                        if (NS == 2) tc::sts_u32x4(off + kTile * C * 2, lo);
+                    }
+                }
+                if (grp == 0) {
+                    const uint32_t nv16 = __float_as_uint((float)n_valid) >> 16;   // small integers are exact in bf16
+                    tc::sts_u32(ab_row + l * L::kAbBytes, nv16 | (nv16 << 16));
+                }
+                tc::cp_async_wait_all();   // this thread's part of W3 has landed
+                tc::fence_proxy_async();
+                tc::fence_before_sync();
+                __syncthreads();
+                issue_round(l, l, sA_addr + (l ^ 1) * L::kABytes, sWb_addr + L::kWbBytes);
+                wait_bar(l);
+            }
+            // ---- final epilogue: out = bev + acc -----------------------------------------------------------------------------
+            __syncwarp();
+            if (R > 0 || p.out != p.bev) {
+                const uint32_t acc_l = tmem_base + (uint32_t)(((R - 1) & 1) * C) + lane_off;
+                float *dst_out = p.out + (size_t)b * C * cells + cell;
+#pragma unroll
+                for (int j = 0; j < (kChunksE + G - 1) / G; ++j) {
+                    const int cc = grp + j * G;
+                    if (cc < kChunksE) {
+                        float z[EW];
+                        if (R > 0) tc::tmem_ld<EW>(acc_l + cc * EW, z);
+                        if (in_range) {
+                            if (j < 2) {
+#pragma unroll
+                                for (int i = 0; i < EW; ++i)
+                                    __stcs(dst_out + (size_t)(cc * EW + i) * cells, R > 0 ? tv[(j & 1) * EW + i] + z[i] : tv[(j & 1) * EW + i]);
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < EW; h += 8) {
+                                    float bv[8];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) bv[i] = __ldcs(src_bev + (size_t)(cc * EW + h + i) * cells);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        __stcs(dst_out + (size_t)(cc * EW + h + i) * cells, R > 0 ? bv[i] + z[h + i] : bv[i]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            cb = nb;
+            cq = nq;
+        }
+        // ---- copy units: cells without a neighbour (back of the list): out = bev ----------------------------------------
+        for (int d = 0; d < 2 && db < p.B; advance(db, dq, (int32_t)gridDim.x)) {
+            const int32_t n_dead = (int32_t)cells - n_live_of(db);
+            if (dq * kTile >= n_dead) continue;
+            ++d;
+            const int32_t j = dq * kTile + row;
+            if (j < n_dead) {
+                const int32_t dc = __ldg(p.cell_list + (size_t)db * cells + (cells - 1 - j));
+                constexpr int CG = C / G;
+                const size_t o = ((size_t)db * C + grp * CG) * cells + dc;
+                const float *src = p.bev + o;
+                float *dst = p.out + o;
+#pragma unroll 1
+                for (int c = 0; c < CG; c += kCopyBatch) {
+                    float v[kCopyBatch];
+#pragma unroll
+                    for (int i = 0; i < kCopyBatch; ++i) {
+                        v[i] = __ldcs(src);
+                        src += cells;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kCopyBatch; ++i) {
+                        __stcs(dst, v[i]);
+                        dst += cells;
+                    }
+                }
+            }
+        }
+    }
+
+    tc::cp_async_wait_all();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K-4a on tensor cores:  T[b, m, :] = feat[b, m, :] W1[:, :Ci]^T + W1[:, Ci:Ci+3] p_m + b1      (m < num_points[b])
 // Tile = 128 points.  W1's image part stays resident in shared memory; the rank-3 offset term and the bias are
 // added on CUDA cores in the epilogue (Ci+3 = 131 is not an MMA-friendly K).
@@ -1106,36 +1503,69 @@ __global__ void __launch_bounds__(kThreads) k_umma_selftest(const float *__restr
     if (warp == 0) tc::tmem_free(tmem_base, N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256);
 }
 
+// CTAs per SM of a persistent fused kernel: every CTA of the grid should be resident at once (static tile -> CTA map), so
+// the count is the minimum over shared memory, registers, threads and TMEM columns (512 per SM, never oversubscribed:
+// a CTA that cannot allocate would spin inside tcgen05.alloc).
+template <typename Kern>
+int resident_ctas(Kern kern, int threads, int smem, int tmem_cols, int *regs_cache, int *out)
+{
+    if (!*regs_cache) {
+        cudaFuncAttributes fa;
+        CF_TRY(cuda_status(cudaFuncGetAttributes(&fa, kern), "fused kernel attributes"));
+        *regs_cache = (fa.numRegs + 7) / 8 * 8;
+    }
+    const int by_smem = (228 * 1024) / (smem + 1024);
+    const int by_regs = 65536 / (*regs_cache * threads);
+    *out = std::max(0, std::min(std::min(std::min(by_smem, by_regs), 2048 / threads), std::min(512 / tmem_cols, 8)));
+    return CF_OK;
+}
+
 template <int C, int NS>
 int launch_tc(const TcParams &p, cudaStream_t st)
 {
     using L = TcLayout<C, NS>;
     constexpr int NT = kTile * TcShape<C>::G;
     const int smem = L::smem_bytes(p.K);
-    static int attr_bytes = 0;
+    static int attr_bytes = 0, regs = 0;
     if (smem > attr_bytes) {
         CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                            "k_fusion_tc smem attribute"));
         attr_bytes = smem;
     }
-    // The kernel is persistent with a static tile -> CTA assignment, so every CTA of the grid should be resident at
-    // once: CTAs per SM = min over shared memory, registers, threads and TMEM columns (512 per SM, never oversubscribed:
-    // a CTA that cannot allocate would spin inside tcgen05.alloc).
-    static int regs_per_thread = 0;
-    if (!regs_per_thread) {
-        cudaFuncAttributes fa;
-        CF_TRY(cuda_status(cudaFuncGetAttributes(&fa, k_fusion_tc<C, NS>), "k_fusion_tc attributes"));
-        regs_per_thread = (fa.numRegs + 7) / 8 * 8;
-    }
-    const int by_smem = (227 * 1024) / (smem + 1024);
-    const int by_regs = 65536 / (regs_per_thread * NT);
-    const int by_tmem = 512 / L::kTmemCols;  // 2 * C columns per CTA, rounded up to a power of two
-    const int by_occ = std::min(std::min(by_smem, by_regs), 2048 / NT);
-    int per_sm = std::max(1, std::min(std::min(by_occ, by_tmem), 8));
+    int per_sm = 1;
+    CF_TRY(resident_ctas(k_fusion_tc<C, NS>, NT, smem, L::kTmemCols, &regs, &per_sm));
+    per_sm = std::max(1, per_sm);
     if (const char *cap = getenv("CF_MAX_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // tuning aid
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
-    if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_tc<%d,%d>: occ %d tmem %d grid %lld smem %d\n", C, NS, by_occ, by_tmem, (long long)grid, smem);
+    if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_tc<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
     k_fusion_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
+    return CF_OK;
+}
+
+// The double-buffered kernel (k_fusion_sk) is used when its shared memory fits and it keeps the residency of k_fusion_tc;
+// returns CF_ERR_UNSUPPORTED (nothing launched) otherwise.  CF_NO_SKEW=1 forces k_fusion_tc (A/B measurements).
+template <int C, int NS>
+int launch_sk(const TcParams &p, cudaStream_t st)
+{
+    using L = SkLayout<C, NS>;
+    using L0 = TcLayout<C, NS>;
+    constexpr int NT = kTile * TcShape<C>::G;
+    const int smem = L::smem_bytes(p.K);
+    if (smem > 227 * 1024 || getenv("CF_NO_SKEW")) return CF_ERR_UNSUPPORTED;
+    static int attr_bytes = 0, regs = 0, regs0 = 0;
+    int per_sm = 0, per_sm0 = 0;
+    CF_TRY(resident_ctas(k_fusion_sk<C, NS>, NT, smem, L::kTmemCols, &regs, &per_sm));
+    CF_TRY(resident_ctas(k_fusion_tc<C, NS>, NT, L0::smem_bytes(p.K), L0::kTmemCols, &regs0, &per_sm0));
+    if (per_sm < 1 || per_sm < per_sm0) return CF_ERR_UNSUPPORTED;
+    if (smem > attr_bytes) {
+        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_sk<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                           "k_fusion_sk smem attribute"));
+        attr_bytes = smem;
+    }
+    if (const char *cap = getenv("CF_MAX_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));
+    const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
+    if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_sk<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
+    k_fusion_sk<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
 
@@ -1208,13 +1638,21 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     case c:                                                                    \
         rc = NS == 2 ? launch_tc<c, 2>(p, st) : launch_tc<c, 1>(p, st);        \
         break;
+#define CF_SK_CASE(c)                                                          \
+    case c:                                                                    \
+        rc = NS == 2 ? launch_sk<c, 2>(p, st) : launch_sk<c, 1>(p, st);        \
+        if (rc == CF_ERR_UNSUPPORTED) rc = NS == 2 ? launch_tc<c, 2>(p, st) : launch_tc<c, 1>(p, st); \
+        break;
     switch (C) {
-        CF_TC_CASE(32) CF_TC_CASE(64) CF_TC_CASE(96) CF_TC_CASE(128) CF_TC_CASE(192) CF_TC_CASE(256)
+        // measured on B200 (profiles/README.md): the double-buffered kernel wins where the MMAs of a round are long
+        // (C = 128: 165 -> 148 us), is a wash at C = 64 and loses at C = 32, where the round is all operand build
+        CF_TC_CASE(32) CF_TC_CASE(64) CF_SK_CASE(96) CF_SK_CASE(128) CF_TC_CASE(192) CF_TC_CASE(256)
         default:
             set_error("cf_fusion_fwd: unsupported C=%d on the tensor-core path", C);
             return CF_ERR_UNSUPPORTED;
     }
 #undef CF_TC_CASE
+#undef CF_SK_CASE
     CF_TRY(rc);
     count_launches(1);
     return launch_status("cf_fusion_fwd (tcgen05)");

@@ -1609,9 +1609,12 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     int32_t *cell_list = cell_count + 128;
     CF_REQUIRE(B <= 64, CF_ERR_ARG, "cf_fusion_fwd: batch %d > 64 frames per call", B);
     const int64_t n_cells = (int64_t)H * W;
-    // Compaction pays when there are many more tiles than SMs; on the small coarse scales it would only reduce the
-    // number of CTAs that have work, so those run every tile (tiles without any neighbour just copy bev -> out).
-    const bool compact = ceil_div64(n_cells, kTile) * B >= 4 * (int64_t)sm_count();
+    // Compaction pays when there are many more tiles than SMs.  On the small coarse scales the cells with a neighbour are
+    // one contiguous blob, so the tiles are already either full or empty (empty tiles just copy bev -> out) and
+    // compaction only adds a launch (measured: 123 -> 148 us at 88x100x192).  CF_COMPACT_MIN_TILES overrides (tuning aid).
+    int64_t min_tiles = 4 * (int64_t)sm_count();
+    if (const char *e = getenv("CF_COMPACT_MIN_TILES")) min_tiles = atoll(e);
+    const bool compact = ceil_div64(n_cells, kTile) * B >= min_tiles;
     if (compact) {
         CF_TRY(cuda_status(cudaMemsetAsync(cell_count, 0, 512, st), "cf_fusion_fwd memset"));
         k_cell_compact<<<dim3((unsigned)ceil_div64(n_cells, 256), (unsigned)B), 256, 0, st>>>(d_knn, K, n_cells, cell_list,

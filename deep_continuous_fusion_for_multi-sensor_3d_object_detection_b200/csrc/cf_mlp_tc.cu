@@ -407,11 +407,38 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     if (p.copy_dead) advance(db, dq, (int32_t)blockIdx.x); else db = p.B;
     if (cb < p.B && grp == 0) header_fill(cb, header_cell(cb, cq), 0);
 
+    // the next two copy units of this CTA: frame (uniform, -1: none left) and this thread's cell (-1: past the end)
+    int32_t uframe[2] = {-1, -1}, ucell[2] = {-1, -1};
+    bool units_ready = false;
+    auto fetch_units = [&]() {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uframe[u] = -1;
+            ucell[u] = -1;
+            int32_t n_dead = 0;
+            while (db < p.B) {
+                n_dead = (int32_t)cells - n_live_of(db);
+                if (dq * kTile < n_dead) break;
+                advance(db, dq, (int32_t)gridDim.x);
+            }
+            if (db < p.B) {
+                uframe[u] = db;
+                const int32_t j = dq * kTile + row;
+                if (j < n_dead) ucell[u] = __ldg(p.cell_list + (size_t)db * cells + (cells - 1 - j));
+                advance(db, dq, (int32_t)gridDim.x);
+            }
+        }
+        units_ready = true;
+    };
+
     while (cb < p.B || db < p.B) {
         if (cb < p.B) {
             const int par = iter & 1;
             ++iter;
             const int b = cb;
+            // list entries of the copy units that follow this tile: in flight during the whole tile (not at C = 32, where
+            // the 4 extra live registers push the mbarrier phase into local memory: 264 -> 283 us)
+            if (C >= 64) fetch_units();
             int32_t nb = cb, nq = cq;
             advance(nb, nq, (int32_t)gridDim.x);
             seek_live(nb, nq);
@@ -641,16 +668,15 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             cq = nq;
         }
         // ---- copy units: cells without a neighbour (back of the list): out = bev ----------------------------------------
-        // (thread = cell, the G thread groups split the channels; two units are interleaved after every MLP tile)
-        for (int d = 0; d < 2 && db < p.B; advance(db, dq, (int32_t)gridDim.x)) {
-            const int32_t n_dead = (int32_t)cells - n_live_of(db);
-            if (dq * kTile >= n_dead) continue;   // uniform: nothing left in this frame's list for this tile slot
-            ++d;
-            const int32_t j = dq * kTile + row;
-            if (j < n_dead) {
-                const int32_t dc = __ldg(p.cell_list + (size_t)db * cells + (cells - 1 - j));
+        // (thread = cell, the G thread groups split the channels; two units are interleaved after every MLP tile; their
+        // list entries were fetched at the start of the tile, so a unit costs one DRAM round trip per channel batch)
+        if (!units_ready) fetch_units();
+        units_ready = false;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (uframe[u] >= 0 && ucell[u] >= 0) {   // uframe is uniform; ucell < 0: a row past the end of the list
                 constexpr int CG = C / G;
-                const size_t o = ((size_t)db * C + grp * CG) * cells + dc;
+                const size_t o = ((size_t)uframe[u] * C + grp * CG) * cells + ucell[u];
                 const float *src = p.bev + o;
                 float *dst = p.out + o;
 #pragma unroll 1
@@ -827,11 +853,35 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     if (p.copy_dead) advance(db, dq, (int32_t)blockIdx.x); else db = p.B;
     if (cb < p.B && grp == 0) header_fill(cb, header_cell(cb, cq), 0);
 
+    int32_t uframe[2] = {-1, -1}, ucell[2] = {-1, -1};   // the next two copy units: frame (uniform) and this thread's cell
+    bool units_ready = false;
+    auto fetch_units = [&]() {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uframe[u] = -1;
+            ucell[u] = -1;
+            int32_t n_dead = 0;
+            while (db < p.B) {
+                n_dead = (int32_t)cells - n_live_of(db);
+                if (dq * kTile < n_dead) break;
+                advance(db, dq, (int32_t)gridDim.x);
+            }
+            if (db < p.B) {
+                uframe[u] = db;
+                const int32_t j = dq * kTile + row;
+                if (j < n_dead) ucell[u] = __ldg(p.cell_list + (size_t)db * cells + (cells - 1 - j));
+                advance(db, dq, (int32_t)gridDim.x);
+            }
+        }
+        units_ready = true;
+    };
+
     while (cb < p.B || db < p.B) {
         if (cb < p.B) {
             const int par = iter & 1;
             ++iter;
             const int b = cb;
+            fetch_units();   // list entries of the copy units that follow this tile: in flight during the whole tile
             int32_t nb = cb, nq = cq;
             advance(nb, nq, (int32_t)gridDim.x);
             seek_live(nb, nq);
@@ -1038,16 +1088,14 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             cb = nb;
             cq = nq;
         }
-        // ---- copy units: cells without a neighbour (back of the list): out = bev ----------------------------------------
-        for (int d = 0; d < 2 && db < p.B; advance(db, dq, (int32_t)gridDim.x)) {
-            const int32_t n_dead = (int32_t)cells - n_live_of(db);
-            if (dq * kTile >= n_dead) continue;
-            ++d;
-            const int32_t j = dq * kTile + row;
-            if (j < n_dead) {
-                const int32_t dc = __ldg(p.cell_list + (size_t)db * cells + (cells - 1 - j));
+        // ---- copy units: cells without a neighbour (back of the list): out = bev (list entries fetched at tile start) ----
+        if (!units_ready) fetch_units();
+        units_ready = false;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (uframe[u] >= 0 && ucell[u] >= 0) {
                 constexpr int CG = C / G;
-                const size_t o = ((size_t)db * C + grp * CG) * cells + dc;
+                const size_t o = ((size_t)uframe[u] * C + grp * CG) * cells + ucell[u];
                 const float *src = p.bev + o;
                 float *dst = p.out + o;
 #pragma unroll 1

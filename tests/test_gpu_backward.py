@@ -130,3 +130,27 @@ def test_training_step_through_the_dropin_model(dcf):
     predicted = lr * gsq
     assert loss1.item() < loss0.item()
     assert abs((loss0.item() - loss1.item()) - predicted) < 0.3 * predicted
+
+
+def test_dropin_model_inference_equals_training_forward(dcf):
+    """Under torch.no_grad() the drop-in model fuses each group's map IN PLACE with tables / KNN precomputed on side
+    streams (one layer-1 launch for all scales); with autograd on it runs the out-of-place path layer by layer.  Both
+    forwards must give the same prediction tensor, bit for bit, and calling the model without the extra tensors must
+    still behave as the LiDAR-only reference."""
+    cfg = dcf.geometry.carla_config(fusion_scales=(1, 2, 3, 4, 5), fusion_k=3, max_num_pc=4096)
+    torch.manual_seed(1)
+    model = dcf.ObjectDetection_DCF(cfg).cuda().eval()
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=2, max_num_pc=4096, n_az=300), seed=23)
+    x_lidar = torch.rand(2, 32, 384, 256, device="cuda")
+    x_image = torch.randint(0, 255, (2, 3, 480, 640), device="cuda", dtype=torch.uint8)
+    extra = dict(pointcloud_raw=dev(wl["points"]), num_points_raw=torch.from_numpy(wl["num_points"]))
+    with torch.no_grad():
+        a = model(x_lidar, x_image, **extra)
+        a2 = model(x_lidar, x_image, **extra)
+        lidar_only = model(x_lidar, x_image)
+    b = model(x_lidar, x_image, **extra)
+    torch.cuda.synchronize()
+    assert b.requires_grad and not a.requires_grad
+    assert torch.equal(a, a2)                       # deterministic, inputs untouched by the in-place fusion
+    assert torch.equal(a, b.detach())
+    assert (a - lidar_only).abs().max() > 1e-4      # the fusion actually contributes

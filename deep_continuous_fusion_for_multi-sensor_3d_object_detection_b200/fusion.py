@@ -15,6 +15,9 @@ from . import geometry as G
 from . import ops
 
 
+_STREAM_POOL = {}   # device index -> side streams, shared by every FrameContext (creating streams per frame is not free)
+
+
 class FrameContext:
     """Per-batch state shared by every fusion scale: bucketed points and gathered camera features."""
 
@@ -29,7 +32,6 @@ class FrameContext:
         self._gather_ws = None
         self._knn_cache = {}
         self._tables = {}      # id(layer) -> (T, ready event): per-scale point tables computed ahead on side streams
-        self._streams = []
         # K-1 runs on a side stream: the camera-feature gather (K-3) does not depend on it, only the KNN search does
         main = torch.cuda.current_stream(self.points.device)
         st = self._side_streams(1)[0]
@@ -80,9 +82,11 @@ class FrameContext:
     # under the backbone's convolutions, in a stand-alone multi-scale call (fuse_scales) they overlap each other.
     # ------------------------------------------------------------------------------------------------------------
     def _side_streams(self, n):
-        while len(self._streams) < n:
-            self._streams.append(torch.cuda.Stream(self.points.device))
-        return self._streams[:n]
+        dev = self.points.device
+        pool = _STREAM_POOL.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(dev))
+        return pool[:n]
 
     def precompute(self, layers, shapes=None):
         """Launch the point tables of `layers` (and, if `shapes` = [(H,W)] is given, their KNN tables) ahead of use.

@@ -8,9 +8,9 @@ kernels behind the C ABI in include/cf_b200.h.  There is no CPU or PyTorch fallb
 """
 from . import dist_util, geometry, synthetic  # noqa: F401  (importable without the CUDA library)
 from ._lib import SO_PATH, build, load  # noqa: F401
-from .fusion import ContinuousFusion, FrameContext, fuse_scales, prepare_frames  # noqa: F401
+from .fusion import ContinuousFusion, FrameContext, FusionRunner, fuse_scales, prepare_frames  # noqa: F401
 from .postprocess import PostProcess  # noqa: F401
 from .model import ObjectDetection_DCF  # noqa: F401
 
-__all__ = ["ContinuousFusion", "FrameContext", "fuse_scales", "prepare_frames", "PostProcess", "ObjectDetection_DCF", "geometry",
+__all__ = ["ContinuousFusion", "FrameContext", "FusionRunner", "fuse_scales", "prepare_frames", "PostProcess", "ObjectDetection_DCF", "geometry",
            "synthetic", "build", "load", "SO_PATH"]

@@ -182,7 +182,9 @@ class PackedWeights:
         key = self._key(W1, mode=m)
         if key != self._key1:
             need = lib.cf_point_mlp1_workspace_bytes(Ci, C_out, m)
-            self._buf1 = torch.empty((need,), dtype=torch.uint8, device=W1.device)
+            if self._buf1 is None or self._buf1.numel() != need or self._buf1.device != W1.device:
+                self._buf1 = torch.empty((need,), dtype=torch.uint8, device=W1.device)   # else: repack in place, so a
+                # CUDA graph that captured this buffer (FusionRunner) sees the refreshed image
             check(lib.cf_point_mlp1_pack_weights(ptr(W1.detach().contiguous()), Ci, C_out, m, ptr(self._buf1), stream_ptr()),
                   "cf_point_mlp1_pack_weights")
             self._key1 = key
@@ -196,7 +198,9 @@ class PackedWeights:
             return None
         key = self._key(W2, W3, mode=m)
         if key != self._key23:
-            self._buf23 = torch.empty((lib.cf_fusion_packed_bytes(Cc, m),), dtype=torch.uint8, device=W2.device)
+            need = lib.cf_fusion_packed_bytes(Cc, m)
+            if self._buf23 is None or self._buf23.numel() != need or self._buf23.device != W2.device:
+                self._buf23 = torch.empty((need,), dtype=torch.uint8, device=W2.device)
             check(lib.cf_fusion_pack_weights(ptr(W2.detach().contiguous()), ptr(W3.detach().contiguous()), Cc, m,
                                              ptr(self._buf23), stream_ptr()), "cf_fusion_pack_weights")
             self._key23 = key

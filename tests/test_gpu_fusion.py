@@ -164,3 +164,42 @@ def test_config2_density_k10_bf16_properties(dcf, oracle):
     ref = oracle.fusion_mlp(sc["bev"][0], feat, pts, knns[4][0], sc["geom"], sc["weights"])
     assert rel_err(outs[4][0], ref) <= 1e-2
     assert rel_err(outs[4][0] - sc["bev"][0], ref - sc["bev"][0]) <= 2e-2
+
+
+def test_fusion_runner_graph_replay_matches_eager(dcf):
+    """FusionRunner (fixed-shape pipeline replayed as one CUDA graph on static buffers, in place) == the eager modules,
+    for two different batches pushed through the same runner."""
+    cfg = dict(dcf.synthetic.workload("yaml"), batch=2, k=3)
+    layers = None
+    runner = None
+    for seed in (31, 32):
+        wl = dcf.synthetic.make_workload(cfg, seed=seed)
+        ref, _ = cuda_fusion(dcf, wl, "fp32")
+        if layers is None:
+            layers = []
+            for sc in wl["scales"]:
+                layer = dcf.ContinuousFusion(wl["img_feat"].shape[1], sc["C"], k=wl["k"], radius=wl["radius"], geom=sc["geom"],
+                                             mode="fp32").cuda()
+                layers.append(layer.eval())
+            grid = dcf.ops.BucketGrid(*dcf.geometry.bucket_grid(wl["config"], None))
+            size = (float(wl["config"]["image_width"]), float(wl["config"]["image_height"]))
+            runner = dcf.FusionRunner(layers, grid, 2, wl["points"].shape[1], wl["img_feat"].shape[1:],
+                                      [sc["bev"].shape[1:] for sc in wl["scales"]], calib=wl["calib"], img_size=size)
+        with torch.no_grad():
+            for layer, sc in zip(layers, wl["scales"]):
+                for prm, w in zip((layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias, layer.fc3.weight,
+                                   layer.fc3.bias), sc["weights"]):
+                    prm.copy_(dev(w))
+        # weights changed in place: the packed operand images must be refreshed before the graph is replayed
+        for layer in layers:
+            layer._packed.w1(layer.fc1.weight, "fp32")
+            layer._packed.w23(layer.fc2.weight, layer.fc3.weight, "fp32")
+        runner.points.copy_(dev(wl["points"]))
+        runner.num_points.copy_(dev(wl["num_points"]))
+        runner.img_feat.copy_(dev(wl["img_feat"]))
+        for d, sc in zip(runner.bevs, wl["scales"]):
+            d.copy_(dev(sc["bev"]))
+        outs = runner()
+        torch.cuda.synchronize()
+        for o, r in zip(outs, ref):
+            assert np.array_equal(o.cpu().numpy(), r)

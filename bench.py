@@ -77,17 +77,31 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled during the timed region: NVML polled every 2 ms from a thread
+    (pynvml), or `nvidia-smi -lms` when NVML is not importable."""
 
     def __init__(self, index=0):
         self.index, self.samples, self.proc, self.thread = index, [], None, None
+        self.stop_flag = threading.Event()
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -95,35 +109,56 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, self.max_sm, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            parts = [p.strip() for p in s.split(",")]
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) < 6:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                self.samples.append((float(parts[0]), float(parts[1]),
+                                     [n for n, v in zip(names, parts[2:6]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+    def mark(self):
+        """Index of the next sample: samples[mark_start:mark_end] are the ones taken inside the timed region."""
+        return len(self.samples)
+
+    def stop(self, lo=0, hi=None):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.01)
+        self.stop_flag.set()
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        window = self.samples[lo:hi] or self.samples
+        sm = [s[0] for s in window]
+        mx = [s[1] for s in window]
+        reasons = set(r for s in window for r in s[2])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ CPU port
@@ -293,14 +328,16 @@ def run_gpu(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    c_lo = sampler.mark()
     e0.record()
     for _ in range(args.steps):
         run_step()
     e1.record()
     barrier()
+    c_hi = sampler.mark()
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(c_lo, c_hi) if rank == 0 else None
 
     # ---- end to end: host buffers in, host buffers out ------------------------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()

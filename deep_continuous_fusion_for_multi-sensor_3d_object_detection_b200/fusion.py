@@ -162,7 +162,12 @@ def fuse_scales(frames, layers, bevs, inplace=False):
         frames.wait_knn()
         outs = list(bevs) if inplace else [torch.empty_like(b) for b in bevs]
         streams = frames._side_streams(len(layers) + 1)[1:]
-        for layer, bev, out, st in zip(layers, bevs, outs, streams):
+        # smallest map first: the coarse scales' kernels are short latency-bound chains on few CTAs, the fine scales' kernels
+        # fill the machine; launching the small ones first lets them run beside the tail of the tables / KNN and of each
+        # other instead of queueing behind the big ones (measured: 4151 -> 4276 frames/s on BASELINE configs[1])
+        order = sorted(range(len(layers)), key=lambda i: bevs[i].numel())
+        for i in order:
+            layer, bev, out, st = layers[i], bevs[i], outs[i], streams[i]
             st.wait_stream(main)
             with torch.cuda.stream(st):
                 layer(bev, frames=frames, out=out)

@@ -162,10 +162,13 @@ def fuse_scales(frames, layers, bevs, inplace=False):
         frames.wait_knn()
         outs = list(bevs) if inplace else [torch.empty_like(b) for b in bevs]
         streams = frames._side_streams(len(layers) + 1)[1:]
-        # smallest map first: the coarse scales' kernels are short latency-bound chains on few CTAs, the fine scales' kernels
-        # fill the machine; launching the small ones first lets them run beside the tail of the tables / KNN and of each
-        # other instead of queueing behind the big ones (measured: 4151 -> 4276 frames/s on BASELINE configs[1])
-        order = sorted(range(len(layers)), key=lambda i: bevs[i].numel())
+        # Launch order.  The coarse scales' kernels are short latency-bound chains on few CTAs, the fine scales' kernels fill
+        # the machine: with several frames per batch, launching the small ones first lets them run beside the tail of the
+        # tables / KNN and of each other instead of queueing behind the big ones (batch 4: 3350 -> 3430 frames/s, batch 8:
+        # 3764 -> 3868); with one or two frames nothing fills the machine and the longest chain should start first
+        # (batch 1: 2087 vs 2118).
+        small_first = bevs[0].shape[0] >= 3
+        order = sorted(range(len(layers)), key=lambda i: bevs[i].numel(), reverse=not small_first)
         for i in order:
             layer, bev, out, st = layers[i], bevs[i], outs[i], streams[i]
             st.wait_stream(main)

@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3]: a full train step of the drop-in ObjectDetection_DCF (LiDAR backbone + camera trunk +
+continuous fusion at every residual group, forward + backward + Adam) on synthetic CARLA-shaped inputs (reference YAML
+grid 384x256, batch 4 per GPU).  The reference's loss.py needs its private dataset's label layout, so the step is closed
+with an MSE on the prediction tensor -- the point here is the cost of the fusion layers inside a train step.
+Single process, or `torchrun --nproc-per-node N` (one process per GPU, DDP all-reduce over NCCL).  Not part of the
+bench contract; prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dcf_b200 as dcf  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--no-fusion", action="store_true", help="LiDAR-only model (the reference as it is) for comparison")
+    a = ap.parse_args()
+    rank, world, local = dcf.dist_util.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dcf.dist_util.init("nccl", dev)
+    cfg = dcf.geometry.carla_config(fusion_scales=(1, 2, 3, 4, 5), fusion_k=3)
+    torch.manual_seed(rank)
+    model = dcf.ObjectDetection_DCF(cfg).to(dev).eval()      # BatchNorm in eval mode, as in the reference (test.py:37)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=a.batch), seed=200 + rank)
+    to = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    x_lidar = torch.rand(a.batch, 32, 384, 256, device=dev)
+    x_image = torch.randint(0, 255, (a.batch, 3, 480, 640), device=dev, dtype=torch.uint8)
+    target = torch.randn(a.batch, 32, 96, 64, device=dev)
+    extra = {} if a.no_fusion else dict(pointcloud_raw=to(wl["points"]), num_points_raw=torch.from_numpy(wl["num_points"]),
+                                        projected_loc_uv=to(wl["uv"]))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pred = model(x_lidar, x_image, **extra)
+        loss = F.mse_loss(pred[:, :18], target[:, :18])
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    dcf.dist_util.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record()
+    dcf.dist_util.barrier()
+    torch.cuda.synchronize()
+    ms = dcf.dist_util.max_over_ranks([e0.elapsed_time(e1) / a.steps], device=dev)[0]
+    if rank == 0:
+        print(json.dumps({"what": "train step (fwd + bwd + Adam), ObjectDetection_DCF, YAML grid 384x256",
+                          "fusion": not a.no_fusion, "batch_per_gpu": a.batch, "n_gpus": world, "ms_per_step": round(ms, 3),
+                          "frames_per_sec": round(a.batch * world / ms * 1e3, 1), "loss": float(loss)}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,15 +121,36 @@ __global__ void __launch_bounds__(256) k_sgemm_tn(const float *__restrict__ A, i
         }
 }
 
-// out[n] += sum_r w[r] * X[r, n]   (w == nullptr: plain column sum);  one block per 256-row slab, atomics at the end
+// out[n] += scale * sum_r w[r] * X[r, n]   (w == nullptr: plain column sum).
+// grid (row slabs of 1024, column chunks of 32); a warp owns every 8th row of the slab, lane = column: 128-byte row
+// segments, 4 independent partial sums per lane, then an 8-warp reduction in shared memory and one atomicAdd per column.
 __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ X, int64_t ldx, int64_t R, int32_t N,
                                                 const float *__restrict__ w, float scale, float *__restrict__ out,
                                                 int64_t out_stride)
 {
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t n = blockIdx.y * 32 + lane;
     const int64_t r_begin = (int64_t)blockIdx.x * 1024, r_end = min(R, r_begin + 1024);
-    for (int32_t n = threadIdx.x; n < N; n += blockDim.x) {
-        float s = 0.0f;
-        for (int64_t r = r_begin; r < r_end; ++r) s = fmaf(w ? __ldg(w + r) : 1.0f, __ldg(X + r * ldx + n), s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (n < N) {
+        int64_t r = r_begin + warp;
+        for (; r + 24 < r_end; r += 32) {
+            const float x0 = __ldg(X + r * ldx + n), x1 = __ldg(X + (r + 8) * ldx + n);
+            const float x2 = __ldg(X + (r + 16) * ldx + n), x3 = __ldg(X + (r + 24) * ldx + n);
+            s0 = fmaf(w ? __ldg(w + r) : 1.0f, x0, s0);
+            s1 = fmaf(w ? __ldg(w + r + 8) : 1.0f, x1, s1);
+            s2 = fmaf(w ? __ldg(w + r + 16) : 1.0f, x2, s2);
+            s3 = fmaf(w ? __ldg(w + r + 24) : 1.0f, x3, s3);
+        }
+        for (; r < r_end; r += 8) s0 = fmaf(w ? __ldg(w + r) : 1.0f, __ldg(X + r * ldx + n), s0);
+    }
+    part[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][lane];
         if (s != 0.0f) atomicAdd(out + (int64_t)n * out_stride, s * scale);
     }
 }
@@ -393,7 +414,7 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     const int64_t split3 = std::max<int64_t>(1024, ceil_div64(ncell, 296));
     k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)ceil_div64(ncell, split3)), 256, 0,
                  st>>>(w.G, C, w.pooled, C, d_gW3, C, ncell, C, C, split3);
-    k_colsum<<<(unsigned)ceil_div64(ncell, 1024), 256, 0, st>>>(w.G, C, ncell, C, w.n_valid, 1.0f, d_gb3, 1);
+    k_colsum<<<dim3((unsigned)ceil_div64(ncell, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.G, C, ncell, C, w.n_valid, 1.0f, d_gb3, 1);
     // dPooled = G W3   (W3 is (out, in) row-major: exactly the [K=out x N=in] operand)
     k_sgemm_nn<<<dim3((unsigned)ceil_div64(ncell, 64), (unsigned)((C + 63) / 64)), 256, 0, st>>>(
         w.G, C, d_W3, C, w.dPooled, C, ncell, C, C, 0, nullptr, 0);
@@ -403,14 +424,14 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     const int64_t split2 = std::max<int64_t>(1024, ceil_div64(rows, 296));
     k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)ceil_div64(rows, split2)), 256, 0,
                  st>>>(w.H2, C, w.H1, C, d_gW2, C, rows, C, C, split2);
-    k_colsum<<<(unsigned)ceil_div64(rows, 1024), 256, 0, st>>>(w.H2, C, rows, C, nullptr, 1.0f, d_gb2, 1);
+    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.H2, C, rows, C, nullptr, 1.0f, d_gb2, 1);
     // dA = (dZ2 W2) * [H1 > 0]   written over H1 (the mask is read before the overwrite, element by element)
     k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), (unsigned)((C + 63) / 64)), 256, 0, st>>>(
         w.H2, C, d_W2, C, w.H1, C, rows, C, C, 0, w.H1, C);
 
     // ---- layer 1: cell-side offset columns, scatter to points, point-side GEMMs -----------------------------------------
-    k_colsum<<<(unsigned)ceil_div64(rows, 1024), 256, 0, st>>>(w.H1, C, rows, C, w.row_cx, -1.0f, d_gW1 + Ci, ldw1);
-    k_colsum<<<(unsigned)ceil_div64(rows, 1024), 256, 0, st>>>(w.H1, C, rows, C, w.row_cy, -1.0f, d_gW1 + Ci + 1, ldw1);
+    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.H1, C, rows, C, w.row_cx, -1.0f, d_gW1 + Ci, ldw1);
+    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.H1, C, rows, C, w.row_cy, -1.0f, d_gW1 + Ci + 1, ldw1);
     CF_TRY(cuda_status(cudaMemsetAsync(w.dT, 0, (size_t)B * N * C * sizeof(float), st), "cf_fusion_bwd memset"));
     k_bwd_scatter<<<dim3(blocks_for(rows_pf, 8), B), 256, 0, st>>>(w.H1, d_knn_idx, N, C, rows_pf, w.dT);
     const int64_t pts = (int64_t)B * N;
@@ -420,7 +441,7 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
                  st>>>(w.dT, C, d_feat, Ci, d_gW1, ldw1, pts, C, Ci, splitp);
     k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), 1, (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(
         w.dT, C, d_points, 3, d_gW1 + Ci, ldw1, pts, C, 3, splitp);
-    k_colsum<<<(unsigned)ceil_div64(pts, 1024), 256, 0, st>>>(w.dT, C, pts, C, nullptr, 1.0f, d_gb1, 1);
+    k_colsum<<<dim3((unsigned)ceil_div64(pts, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.dT, C, pts, C, nullptr, 1.0f, d_gb1, 1);
     // dF += dT W1[:, :Ci]
     k_sgemm_nn<<<dim3((unsigned)ceil_div64(pts, 64), (unsigned)((Ci + 63) / 64)), 256, 0, st>>>(
         w.dT, C, d_W1, ldw1, d_gfeat, Ci, pts, Ci, C, 1, nullptr, 0);

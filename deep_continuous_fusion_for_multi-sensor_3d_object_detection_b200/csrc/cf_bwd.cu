@@ -12,9 +12,11 @@
 //   dW1[:, Ci]   -= sum_r dA_r cx_r           dW1[:, Ci+1] -= sum_r dA_r cy_r
 //   dW1[:, :Ci] += dT^T F     dW1[:, Ci:] += dT^T P     db1 += sum_p dT_p     dF += dT W1[:, :Ci]
 // Nothing is saved by the forward except indices, inputs and weights: H1, H2 and pooled are recomputed here and
-// materialised in the caller-provided workspace (dense (cell,k) rows, zero for empty slots).  All arithmetic is
-// fp32 on CUDA cores (this is the round-1 "correct first" implementation; reductions over rows use split
-// accumulation + atomics, so gradients are reproducible to rounding, not bit for bit).
+// materialised in the caller-provided workspace.  Only (cell, k) slots that HOLD a neighbour exist there: k_bwd_compact
+// turns knn_idx into a list of live cells and a list of live rows (the rows of a cell are contiguous), their two counts
+// stay in device memory, and every later kernel is launched for the dense upper bound and clamps itself to the count
+// (no host synchronisation; blocks beyond the count exit at once).  All arithmetic is fp32 on CUDA cores; reductions
+// over rows use split accumulation + atomics, so gradients are reproducible to rounding, not bit for bit.
 #include "cf_common.cuh"
 
 namespace cf {
@@ -26,13 +28,16 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sgemm_nn(const float *__restrict__ A, int64_t lda, const float *__restrict__ Bm,
                                                   int64_t ldb, float *__restrict__ Cm, int64_t ldc, int64_t R, int32_t N,
-                                                  int32_t Kd, int beta, const float *__restrict__ mask, int64_t ldm)
+                                                  int32_t Kd, int beta, const float *__restrict__ mask, int64_t ldm,
+                                                  const int32_t *__restrict__ d_R)
 {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t r0 = (int64_t)blockIdx.x * 64;
     const int32_t n0 = blockIdx.y * 64;
+    if (d_R) R = min(R, (int64_t)__ldg(d_R));
+    if (r0 >= R) return;
     float acc[4][4] = {};
     for (int32_t k0 = 0; k0 < Kd; k0 += 16) {
 #pragma unroll
@@ -82,13 +87,15 @@ __global__ void __launch_bounds__(256) k_sgemm_nn(const float *__restrict__ A, i
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sgemm_tn(const float *__restrict__ A, int64_t lda, const float *__restrict__ Bm,
                                                   int64_t ldb, float *__restrict__ Cm, int64_t ldc, int64_t R, int32_t M,
-                                                  int32_t N, int64_t rows_per_split)
+                                                  int32_t N, int64_t rows_per_split, const int32_t *__restrict__ d_R)
 {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int32_t m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    if (d_R) R = min(R, (int64_t)__ldg(d_R));
     const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split, r_end = min(R, r_begin + rows_per_split);
+    if (r_begin >= R) return;
     float acc[4][4] = {};
     for (int64_t r0 = r_begin; r0 < r_end; r0 += 16) {
 #pragma unroll
@@ -126,12 +133,14 @@ __global__ void __launch_bounds__(256) k_sgemm_tn(const float *__restrict__ A, i
 // segments, 4 independent partial sums per lane, then an 8-warp reduction in shared memory and one atomicAdd per column.
 __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ X, int64_t ldx, int64_t R, int32_t N,
                                                 const float *__restrict__ w, float scale, float *__restrict__ out,
-                                                int64_t out_stride)
+                                                int64_t out_stride, const int32_t *__restrict__ d_R)
 {
     __shared__ float part[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t n = blockIdx.y * 32 + lane;
+    if (d_R) R = min(R, (int64_t)__ldg(d_R));
     const int64_t r_begin = (int64_t)blockIdx.x * 1024, r_end = min(R, r_begin + 1024);
+    if (r_begin >= R) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (n < N) {
         int64_t r = r_begin + warp;
@@ -155,82 +164,136 @@ __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ X, int
     }
 }
 
-// (B, C, cells) -> (B, cells, C)
-__global__ void __launch_bounds__(256) k_nchw_to_cell_major(const float *__restrict__ src, int32_t C, int64_t cells,
-                                                            float *__restrict__ dst)
+// Live-cell / live-row lists.  Thread = cell (all frames in one index space).  A cell with n > 0 neighbours takes the next
+// free cell slot ci and n consecutive row slots (block-wide ballot / shuffle scan, one atomicAdd per block and counter).
+//   cell_list[ci] = b * cells + cell     cell_row0[ci] = first row     cell_nv[ci] = n  (float: it multiplies b3's gradient)
+//   row_pt[r] = b * N + point            row_cell[r] = ci              row_cx / row_cy[r] = the cell's centre
+// counters[0] = live cells, counters[1] = live rows (zeroed by the caller of the kernel).
+__global__ void __launch_bounds__(256) k_bwd_compact(const int32_t *__restrict__ knn, int64_t ncell, int64_t cells, int32_t W,
+                                                     int32_t K, int32_t N, float x0, float y0, float dx, float dy,
+                                                     int32_t *__restrict__ counters, int32_t *__restrict__ cell_list,
+                                                     int32_t *__restrict__ cell_row0, float *__restrict__ cell_nv,
+                                                     int32_t *__restrict__ row_pt, int32_t *__restrict__ row_cell,
+                                                     float *__restrict__ row_cx, float *__restrict__ row_cy)
+{
+    __shared__ int32_t warp_cells[8], warp_rows[8], base[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int32_t nv = 0;
+    if (g < ncell)
+        for (int k = 0; k < K; ++k) nv += __ldg(knn + g * K + k) >= 0;
+    const unsigned live = __ballot_sync(0xffffffffu, nv > 0);
+    int32_t incl = nv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) {
+        warp_cells[warp] = __popc(live);
+        warp_rows[warp] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t c = 0, r = 0;
+        for (int i = 0; i < 8; ++i) {
+            const int32_t tc = warp_cells[i], tr = warp_rows[i];
+            warp_cells[i] = c;
+            warp_rows[i] = r;
+            c += tc;
+            r += tr;
+        }
+        base[0] = c ? atomicAdd(counters, c) : 0;
+        base[1] = r ? atomicAdd(counters + 1, r) : 0;
+    }
+    __syncthreads();
+    if (nv == 0) return;
+    const int32_t ci = base[0] + warp_cells[warp] + __popc(live & ((1u << lane) - 1u));
+    int32_t r = base[1] + warp_rows[warp] + incl - nv;
+    const int32_t b = (int32_t)(g / cells);
+    const int64_t cell = g - (int64_t)b * cells;
+    const int32_t i = (int32_t)(cell / W), j = (int32_t)(cell - (int64_t)i * W);
+    const float cx = __fadd_rn(x0, __fmul_rn((float)i, dx)), cy = __fadd_rn(y0, __fmul_rn((float)j, dy));
+    cell_list[ci] = (int32_t)g;
+    cell_row0[ci] = r;
+    cell_nv[ci] = (float)nv;
+    for (int k = 0; k < K; ++k) {
+        const int32_t p = __ldg(knn + g * K + k);
+        if (p < 0) continue;
+        row_pt[r] = b * N + p;
+        row_cell[r] = ci;
+        row_cx[r] = cx;
+        row_cy[r] = cy;
+        ++r;
+    }
+}
+
+// G[ci, c] = gout[b, c, cell] for the live cells (32 cells x 32 channels per block through a shared-memory transpose;
+// list neighbours are mostly grid neighbours, so the reads of a warp still fall into few lines)
+__global__ void __launch_bounds__(256) k_bwd_gather_g(const float *__restrict__ gout, int32_t C, int64_t cells,
+                                                      const int32_t *__restrict__ cell_list,
+                                                      const int32_t *__restrict__ counters, float *__restrict__ G)
 {
     __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const int64_t p0 = (int64_t)blockIdx.x * 32;
-    const int32_t c0 = blockIdx.y * 32;
+    const int32_t n = __ldg(counters);
+    const int32_t t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    if (t0 >= n) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int32_t ci = t0 + tx;
+    int64_t src = -1;
+    if (ci < n) {
+        const int64_t g = __ldg(cell_list + ci);
+        const int64_t b = g / cells;
+        src = (b * C) * cells + (g - b * cells);
+    }
     for (int r = ty; r < 32; r += 8) {
         const int32_t c = c0 + r;
-        const int64_t p = p0 + tx;
-        tile[r][tx] = (c < C && p < cells) ? __ldg(src + ((size_t)b * C + c) * cells + p) : 0.0f;
+        tile[r][tx] = (src >= 0 && c < C) ? __ldg(gout + src + (int64_t)c * cells) : 0.0f;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
-        const int64_t p = p0 + r;
         const int32_t c = c0 + tx;
-        if (p < cells && c < C) dst[((size_t)b * cells + p) * C + c] = tile[tx][r];
+        if (t0 + r < n && c < C) G[(size_t)(t0 + r) * C + c] = tile[tx][r];
     }
 }
 
-// Recompute H1 rows: H1[(b,cell,k), c] = relu(T[b, j, c] - w1x[c] cx - w1y[c] cy) (0 for an empty slot); also the
-// per-row cell centre (for the offset-column gradients) and per-cell n_valid.
-__global__ void __launch_bounds__(256) k_bwd_h1(const float *__restrict__ T, const int32_t *__restrict__ knn, int32_t N,
-                                                int32_t C, int32_t H, int32_t W, int32_t K, float x0, float y0, float dx,
-                                                float dy, const float *__restrict__ W1, int32_t Ci,
-                                                float *__restrict__ H1, float *__restrict__ row_cx,
-                                                float *__restrict__ row_cy, float *__restrict__ n_valid)
+// Recompute H1 rows (one warp per live row): H1[r, c] = relu(T[pt_r, c] - w1x[c] cx_r - w1y[c] cy_r)
+__global__ void __launch_bounds__(256) k_bwd_h1(const float *__restrict__ T, const int32_t *__restrict__ row_pt,
+                                                const float *__restrict__ row_cx, const float *__restrict__ row_cy,
+                                                const int32_t *__restrict__ counters, int32_t C,
+                                                const float *__restrict__ W1, int32_t Ci, float *__restrict__ H1)
 {
-    const int b = blockIdx.y;
-    const int64_t cells = (int64_t)H * W, rows = cells * K;
+    const int32_t rows = __ldg(counters + 1);
     const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
-        const int64_t cell = r / K;
-        const int32_t k = (int32_t)(r - cell * K);
-        const int32_t i = (int32_t)(cell / W), j = (int32_t)(cell - (int64_t)i * W);
-        const float cx = __fadd_rn(x0, __fmul_rn((float)i, dx)), cy = __fadd_rn(y0, __fmul_rn((float)j, dy));
-        const int32_t p = __ldg(knn + ((size_t)b * cells + cell) * K + k);
-        float *h = H1 + ((size_t)b * rows + r) * C;
+    const int32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (int32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+        const float cx = __ldg(row_cx + r), cy = __ldg(row_cy + r);
+        const float *t = T + (size_t)__ldg(row_pt + r) * C;
+        float *h = H1 + (size_t)r * C;
         for (int32_t c = lane; c < C; c += 32) {
-            float v = 0.0f;
-            if (p >= 0) {
-                const float *w = W1 + (size_t)c * (Ci + 3) + Ci;
-                v = fmaxf(__ldg(T + ((size_t)b * N + p) * C + c) - (__ldg(w) * cx + __ldg(w + 1) * cy), 0.0f);
-            }
-            h[c] = v;
-        }
-        if (lane == 0) {
-            row_cx[(size_t)b * rows + r] = p >= 0 ? cx : 0.0f;
-            row_cy[(size_t)b * rows + r] = p >= 0 ? cy : 0.0f;
-            if (k == 0) {
-                int nv = 0;
-                for (int kk = 0; kk < K; ++kk) nv += __ldg(knn + ((size_t)b * cells + cell) * K + kk) >= 0;
-                n_valid[(size_t)b * cells + cell] = (float)nv;
-            }
+            const float *w = W1 + (size_t)c * (Ci + 3) + Ci;
+            h[c] = fmaxf(__ldg(t + c) - (__ldg(w) * cx + __ldg(w + 1) * cy), 0.0f);
         }
     }
 }
 
-// H2[r, c] = valid(r) ? relu(Z[r, c] + b2[c]) : 0 (in place on Z);  pooled[cell, c] = sum_k H2
-__global__ void __launch_bounds__(256) k_bwd_h2_pool(float *__restrict__ Z, const int32_t *__restrict__ knn_flat,
-                                                     const float *__restrict__ b2, int64_t n_cells_total, int32_t K,
-                                                     int32_t C, float *__restrict__ pooled)
+// H2[r, c] = relu(Z[r, c] + b2[c]) (in place on Z);  pooled[ci, c] = sum over the cell's rows
+__global__ void __launch_bounds__(256) k_bwd_h2_pool(float *__restrict__ Z, const int32_t *__restrict__ cell_row0,
+                                                     const float *__restrict__ cell_nv, const float *__restrict__ b2,
+                                                     const int32_t *__restrict__ counters, int32_t C,
+                                                     float *__restrict__ pooled)
 {
-    const int64_t total = n_cells_total * C;
+    const int64_t total = (int64_t)__ldg(counters) * C;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t cell = t / C;
-        const int32_t c = (int32_t)(t - cell * C);
+        const int64_t ci = t / C;
+        const int32_t c = (int32_t)(t - ci * C);
+        const int64_t r0 = __ldg(cell_row0 + ci);
+        const int32_t nv = (int32_t)__ldg(cell_nv + ci);
+        const float bias = __ldg(b2 + c);
         float s = 0.0f;
-        for (int k = 0; k < K; ++k) {
-            const int64_t r = cell * K + k;
-            const bool valid = __ldg(knn_flat + r) >= 0;
-            const float h = valid ? fmaxf(Z[r * C + c] + __ldg(b2 + c), 0.0f) : 0.0f;
-            Z[r * C + c] = h;
+        for (int k = 0; k < nv; ++k) {
+            const float h = fmaxf(Z[(r0 + k) * C + c] + bias, 0.0f);
+            Z[(r0 + k) * C + c] = h;
             s += h;
         }
         pooled[t] = s;
@@ -238,29 +301,29 @@ __global__ void __launch_bounds__(256) k_bwd_h2_pool(float *__restrict__ Z, cons
 }
 
 // dZ2[r, c] = dPooled[cell(r), c] * [H2[r, c] > 0]   (in place on H2)
-__global__ void __launch_bounds__(256) k_bwd_dz2(float *__restrict__ H2, const float *__restrict__ dPooled, int64_t rows,
-                                                 int32_t K, int32_t C)
+__global__ void __launch_bounds__(256) k_bwd_dz2(float *__restrict__ H2, const float *__restrict__ dPooled,
+                                                 const int32_t *__restrict__ row_cell,
+                                                 const int32_t *__restrict__ counters, int32_t C)
 {
-    const int64_t total = rows * C;
+    const int64_t total = (int64_t)__ldg(counters + 1) * C;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = t / C;
         const int32_t c = (int32_t)(t - r * C);
-        H2[t] = H2[t] > 0.0f ? __ldg(dPooled + (r / K) * C + c) : 0.0f;
+        H2[t] = H2[t] > 0.0f ? __ldg(dPooled + (size_t)__ldg(row_cell + r) * C + c) : 0.0f;
     }
 }
 
-// dT[b, j_r, :] += dA[r, :]   (one warp per row, float atomics)
-__global__ void __launch_bounds__(256) k_bwd_scatter(const float *__restrict__ dA, const int32_t *__restrict__ knn, int32_t N,
-                                                     int32_t C, int64_t rows_per_frame, float *__restrict__ dT)
+// dT[pt_r, :] += dA[r, :]   (one warp per live row, float atomics)
+__global__ void __launch_bounds__(256) k_bwd_scatter(const float *__restrict__ dA, const int32_t *__restrict__ row_pt,
+                                                     const int32_t *__restrict__ counters, int32_t C,
+                                                     float *__restrict__ dT)
 {
-    const int b = blockIdx.y;
+    const int32_t rows = __ldg(counters + 1);
     const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_per_frame; r += warps) {
-        const int32_t p = __ldg(knn + (size_t)b * rows_per_frame + r);
-        if (p < 0) continue;
-        const float *src = dA + ((size_t)b * rows_per_frame + r) * C;
-        float *dst = dT + ((size_t)b * N + p) * C;
+    const int32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (int32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+        const float *src = dA + (size_t)r * C;
+        float *dst = dT + (size_t)__ldg(row_pt + r) * C;
         for (int32_t c = lane; c < C; c += 32) {
             const float v = __ldg(src + c);
             if (v != 0.0f) atomicAdd(dst + c, v);
@@ -321,31 +384,38 @@ __global__ void __launch_bounds__(256) k_point_gather_bwd(const float *__restric
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct BwdWs {
-    float *H1, *H2, *pooled, *G, *dPooled, *row_cx, *row_cy, *n_valid, *T, *dT, *W2t;
+    float *H1, *H2, *pooled, *G, *dPooled, *row_cx, *row_cy, *cell_nv, *T, *dT, *W2t;
+    int32_t *cell_list, *cell_row0, *row_pt, *row_cell, *counters;
     size_t bytes;
 };
 
+// sized for the dense upper bound (every slot of every cell holds a neighbour)
 static BwdWs carve(void *base, int32_t B, int32_t N, int32_t C, int64_t cells, int32_t K)
 {
     BwdWs w;
     size_t off = 0;
-    auto take = [&](size_t n_floats) {
-        float *p = base ? (float *)((char *)base + off) : nullptr;
-        off += up256(n_floats * sizeof(float));
+    auto take = [&](size_t n_words) {
+        void *p = base ? (void *)((char *)base + off) : nullptr;
+        off += up256(n_words * 4);
         return p;
     };
     const size_t rows = (size_t)B * cells * K, ncell = (size_t)B * cells;
-    w.H1 = take(rows * C);
-    w.H2 = take(rows * C);
-    w.pooled = take(ncell * C);
-    w.G = take(ncell * C);
-    w.dPooled = take(ncell * C);
-    w.row_cx = take(rows);
-    w.row_cy = take(rows);
-    w.n_valid = take(ncell);
-    w.T = take((size_t)B * N * C);
-    w.dT = take((size_t)B * N * C);
-    w.W2t = take((size_t)C * C);
+    w.H1 = (float *)take(rows * C);
+    w.H2 = (float *)take(rows * C);
+    w.pooled = (float *)take(ncell * C);
+    w.G = (float *)take(ncell * C);
+    w.dPooled = (float *)take(ncell * C);
+    w.row_cx = (float *)take(rows);
+    w.row_cy = (float *)take(rows);
+    w.cell_nv = (float *)take(ncell);
+    w.T = (float *)take((size_t)B * N * C);
+    w.dT = (float *)take((size_t)B * N * C);
+    w.W2t = (float *)take((size_t)C * C);
+    w.cell_list = (int32_t *)take(ncell);
+    w.cell_row0 = (int32_t *)take(ncell);
+    w.row_pt = (int32_t *)take(rows);
+    w.row_cell = (int32_t *)take(rows);
+    w.counters = (int32_t *)take(2);
     w.bytes = off;
     return w;
 }
@@ -394,58 +464,68 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
                CF_ERR_ARG, "cf_fusion_bwd: bad extents");
     CF_REQUIRE(aligned16(d_workspace), CF_ERR_ALIGN, "cf_fusion_bwd: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t cells = (int64_t)H * W, ncell = cells * B, rows_pf = cells * K, rows = rows_pf * B;
+    const int64_t cells = (int64_t)H * W, ncell = cells * B, rows = cells * K * B;
+    CF_REQUIRE(rows < (int64_t)1 << 31 && (int64_t)B * N < (int64_t)1 << 31, CF_ERR_ARG,
+               "cf_fusion_bwd: B*H*W*K and B*N must stay below 2^31");
     BwdWs w = carve(d_workspace, B, N, C, cells, K);
     const int32_t ldw1 = Ci + 3;
+    const int32_t *n_cells = w.counters, *n_rows = w.counters + 1;
+    const unsigned cchunks = (unsigned)((C + 31) / 32), ctiles = (unsigned)((C + 63) / 64);
 
-    // ---- recompute the forward intermediates ------------------------------------------------------------------------
+    // ---- live cells / rows, then the forward intermediates on them ----------------------------------------------------
+    CF_TRY(cuda_status(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int32_t), st), "cf_fusion_bwd memset"));
+    k_bwd_compact<<<(unsigned)ceil_div64(ncell, 256), 256, 0, st>>>(d_knn_idx, ncell, cells, W, K, N, x0, y0, dx, dy, w.counters,
+                                                                   w.cell_list, w.cell_row0, w.cell_nv, w.row_pt, w.row_cell,
+                                                                   w.row_cx, w.row_cy);
     CF_TRY(point_mlp1_simt(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, w.T, st));
-    k_bwd_h1<<<dim3(blocks_for(rows_pf, 8), B), 256, 0, st>>>(w.T, d_knn_idx, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, w.H1,
-                                                            w.row_cx, w.row_cy, w.n_valid);
+    k_bwd_h1<<<blocks_for(rows, 8), 256, 0, st>>>(w.T, w.row_pt, w.row_cx, w.row_cy, w.counters, C, d_W1, Ci, w.H1);
     k_transpose_sq_b<<<(C * C + 255) / 256, 256, 0, st>>>(d_W2, C, w.W2t);
     // Z2 = H1 W2^T  (as  H1 [rows x C] * W2t [C x C])
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), (unsigned)((C + 63) / 64)), 256, 0, st>>>(
-        w.H1, C, w.W2t, C, w.H2, C, rows, C, C, 0, nullptr, 0);
-    k_bwd_h2_pool<<<blocks_for(ncell * C, 256), 256, 0, st>>>(w.H2, d_knn_idx, d_b2, ncell, K, C, w.pooled);
+    k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H1, C, w.W2t, C, w.H2, C, rows, C, C, 0, nullptr,
+                                                                            0, n_rows);
+    k_bwd_h2_pool<<<blocks_for(ncell * C, 256), 256, 0, st>>>(w.H2, w.cell_row0, w.cell_nv, d_b2, w.counters, C, w.pooled);
 
     // ---- layer 3 ------------------------------------------------------------------------------------------------------
-    k_nchw_to_cell_major<<<dim3((unsigned)ceil_div64(cells, 32), (unsigned)((C + 31) / 32), (unsigned)B), 256, 0, st>>>(
-        d_gout, C, cells, w.G);
-    const int64_t split3 = std::max<int64_t>(1024, ceil_div64(ncell, 296));
-    k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)ceil_div64(ncell, split3)), 256, 0,
-                 st>>>(w.G, C, w.pooled, C, d_gW3, C, ncell, C, C, split3);
-    k_colsum<<<dim3((unsigned)ceil_div64(ncell, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.G, C, ncell, C, w.n_valid, 1.0f, d_gb3, 1);
+    k_bwd_gather_g<<<dim3((unsigned)ceil_div64(ncell, 32), cchunks), 256, 0, st>>>(d_gout, C, cells, w.cell_list, w.counters,
+                                                                                  w.G);
+    const int64_t split3 = std::max<int64_t>(256, ceil_div64(ncell, 1184));
+    k_sgemm_tn<<<dim3(ctiles, ctiles, (unsigned)ceil_div64(ncell, split3)), 256, 0, st>>>(w.G, C, w.pooled, C, d_gW3, C, ncell, C,
+                                                                                         C, split3, n_cells);
+    k_colsum<<<dim3((unsigned)ceil_div64(ncell, 1024), cchunks), 256, 0, st>>>(w.G, C, ncell, C, w.cell_nv, 1.0f, d_gb3, 1,
+                                                                              n_cells);
     // dPooled = G W3   (W3 is (out, in) row-major: exactly the [K=out x N=in] operand)
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(ncell, 64), (unsigned)((C + 63) / 64)), 256, 0, st>>>(
-        w.G, C, d_W3, C, w.dPooled, C, ncell, C, C, 0, nullptr, 0);
+    k_sgemm_nn<<<dim3((unsigned)ceil_div64(ncell, 64), ctiles), 256, 0, st>>>(w.G, C, d_W3, C, w.dPooled, C, ncell, C, C, 0,
+                                                                             nullptr, 0, n_cells);
 
     // ---- layer 2 ------------------------------------------------------------------------------------------------------
-    k_bwd_dz2<<<blocks_for(rows * C, 256), 256, 0, st>>>(w.H2, w.dPooled, rows, K, C);  // H2 now holds dZ2
-    const int64_t split2 = std::max<int64_t>(1024, ceil_div64(rows, 296));
-    k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)ceil_div64(rows, split2)), 256, 0,
-                 st>>>(w.H2, C, w.H1, C, d_gW2, C, rows, C, C, split2);
-    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.H2, C, rows, C, nullptr, 1.0f, d_gb2, 1);
+    k_bwd_dz2<<<blocks_for(rows * C, 256), 256, 0, st>>>(w.H2, w.dPooled, w.row_cell, w.counters, C);  // H2 now holds dZ2
+    const int64_t split2 = std::max<int64_t>(256, ceil_div64(rows, 1184));
+    k_sgemm_tn<<<dim3(ctiles, ctiles, (unsigned)ceil_div64(rows, split2)), 256, 0, st>>>(w.H2, C, w.H1, C, d_gW2, C, rows, C, C,
+                                                                                        split2, n_rows);
+    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H2, C, rows, C, nullptr, 1.0f, d_gb2, 1, n_rows);
     // dA = (dZ2 W2) * [H1 > 0]   written over H1 (the mask is read before the overwrite, element by element)
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), (unsigned)((C + 63) / 64)), 256, 0, st>>>(
-        w.H2, C, d_W2, C, w.H1, C, rows, C, C, 0, w.H1, C);
+    k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H2, C, d_W2, C, w.H1, C, rows, C, C, 0, w.H1, C,
+                                                                            n_rows);
 
     // ---- layer 1: cell-side offset columns, scatter to points, point-side GEMMs -----------------------------------------
-    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.H1, C, rows, C, w.row_cx, -1.0f, d_gW1 + Ci, ldw1);
-    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.H1, C, rows, C, w.row_cy, -1.0f, d_gW1 + Ci + 1, ldw1);
+    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H1, C, rows, C, w.row_cx, -1.0f, d_gW1 + Ci, ldw1,
+                                                                             n_rows);
+    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H1, C, rows, C, w.row_cy, -1.0f, d_gW1 + Ci + 1,
+                                                                             ldw1, n_rows);
     CF_TRY(cuda_status(cudaMemsetAsync(w.dT, 0, (size_t)B * N * C * sizeof(float), st), "cf_fusion_bwd memset"));
-    k_bwd_scatter<<<dim3(blocks_for(rows_pf, 8), B), 256, 0, st>>>(w.H1, d_knn_idx, N, C, rows_pf, w.dT);
+    k_bwd_scatter<<<blocks_for(rows, 8), 256, 0, st>>>(w.H1, w.row_pt, w.counters, C, w.dT);
     const int64_t pts = (int64_t)B * N;
     const int64_t splitp = std::max<int64_t>(512, ceil_div64(pts, 148));
     // feat / points rows beyond num_points are never referenced by knn, so their dT rows are zero
-    k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), (unsigned)((Ci + 63) / 64), (unsigned)ceil_div64(pts, splitp)), 256, 0,
-                 st>>>(w.dT, C, d_feat, Ci, d_gW1, ldw1, pts, C, Ci, splitp);
-    k_sgemm_tn<<<dim3((unsigned)((C + 63) / 64), 1, (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(
-        w.dT, C, d_points, 3, d_gW1 + Ci, ldw1, pts, C, 3, splitp);
-    k_colsum<<<dim3((unsigned)ceil_div64(pts, 1024), (unsigned)((C + 31) / 32)), 256, 0, st>>>(w.dT, C, pts, C, nullptr, 1.0f, d_gb1, 1);
+    k_sgemm_tn<<<dim3(ctiles, (unsigned)((Ci + 63) / 64), (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(
+        w.dT, C, d_feat, Ci, d_gW1, ldw1, pts, C, Ci, splitp, nullptr);
+    k_sgemm_tn<<<dim3(ctiles, 1, (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(w.dT, C, d_points, 3, d_gW1 + Ci, ldw1, pts,
+                                                                                  C, 3, splitp, nullptr);
+    k_colsum<<<dim3((unsigned)ceil_div64(pts, 1024), cchunks), 256, 0, st>>>(w.dT, C, pts, C, nullptr, 1.0f, d_gb1, 1, nullptr);
     // dF += dT W1[:, :Ci]
     k_sgemm_nn<<<dim3((unsigned)ceil_div64(pts, 64), (unsigned)((Ci + 63) / 64)), 256, 0, st>>>(
-        w.dT, C, d_W1, ldw1, d_gfeat, Ci, pts, Ci, C, 1, nullptr, 0);
-    count_launches(18);
+        w.dT, C, d_W1, ldw1, d_gfeat, Ci, pts, Ci, C, 1, nullptr, 0, nullptr);
+    count_launches(19);
     return launch_status("cf_fusion_bwd");
 }
 

@@ -13,7 +13,7 @@ CSRC = os.path.join(_PKG, "csrc")
 MODE_FP32, MODE_BF16, MODE_SIMT = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "simt": MODE_SIMT}
 MAX_K = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -41,9 +41,9 @@ SIGNATURES = {
     "cf_fusion_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cf_fusion_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _i32,
                                 _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
-    "cf_fusion_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "cf_fusion_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "cf_fusion_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32,
-                                _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "cf_point_gather_bwd": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp,
                                       C.POINTER(C.c_float), _vp, _i32, _f32, _f32, _vp]),
     "cf_voxelize_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
@@ -56,6 +56,9 @@ SIGNATURES = {
     "cf_sat_matrix": (C.c_int, [_vp, _i32, _vp, _vp]),
     "cf_box_iou": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp]),
     "cf_debug_umma_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "cf_debug_bwd_packed_bytes": (_sz, [_i32, _i32]),
+    "cf_debug_bwd_gemm_nn": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "cf_debug_bwd_gemm_tn": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

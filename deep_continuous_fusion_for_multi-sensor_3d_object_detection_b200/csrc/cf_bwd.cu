@@ -9,8 +9,8 @@
 //   dW3 += G^T pooled        db3 += sum_c n_valid(c) G_c        dPooled = G W3
 //   dZ2_r = dPooled_cell(r) * [h2_r > 0]      dW2 += dZ2^T H1      db2 += sum_r dZ2_r
 //   dA_r  = (dZ2_r W2) * [h1_r > 0]           dT[j_r] += dA_r  (scatter-add, atomics)
-//   dW1[:, Ci]   -= sum_r dA_r cx_r           dW1[:, Ci+1] -= sum_r dA_r cy_r
-//   dW1[:, :Ci] += dT^T F     dW1[:, Ci:] += dT^T P     db1 += sum_p dT_p     dF += dT W1[:, :Ci]
+//   dW1[:, Ci + j] += sum_r dA_r off_j(r),  off = (px - cx, py - cy, pz) of row r
+//   dW1[:, :Ci] += dT^T F     db1 += sum_p dT_p     dF += dT W1[:, :Ci]
 // Nothing is saved by the forward except indices, inputs and weights: H1, H2 and pooled are recomputed here and
 // materialised in the caller-provided workspace.  Only (cell, k) slots that HOLD a neighbour exist there: k_bwd_compact
 // turns knn_idx into a list of live cells and a list of live rows (the rows of a cell are contiguous), their two counts
@@ -20,6 +20,18 @@
 #include "cf_common.cuh"
 
 namespace cf {
+
+// cf_bwd_tc.cu: the same GEMMs on the tcgen05 tensor cores (fp32 operands split into bf16 hi + lo, fp32 accumulate)
+enum { EPI_STORE = 0, EPI_ACCUM = 1, EPI_BIAS_RELU = 2, EPI_MASK = 3 };
+size_t bwd_tc_packed_bytes(int32_t Nn, int32_t Kd);
+bool bwd_tc_nn_fits(int32_t Kd, int32_t N);
+bool bwd_tc_tn_fits(int32_t M, int32_t N);
+int bwd_tc_pack(const float *d_W, int32_t ld, int32_t Nn, int32_t Kd, int transpose, void *d_img, cudaStream_t st);
+int bwd_tc_gemm_nn(const float *X, int64_t ldx, int64_t R, const int32_t *d_R, int32_t Kd, int32_t N, const void *wimg,
+                   float *Out, int64_t ldo, int epi, const float *aux, int64_t ldaux, cudaStream_t st);
+int bwd_tc_gemm_tn(const float *X, int64_t ldx, int32_t M, const float *Y, int64_t ldy, int32_t N, const float *Y2,
+                   int64_t rs2, int64_t cs2, int32_t n2, const float *wcol, int64_t R, const int32_t *d_R, float *dW,
+                   int64_t ldw, float *db, cudaStream_t st);
 
 namespace {
 
@@ -168,13 +180,16 @@ __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ X, int
 // free cell slot ci and n consecutive row slots (block-wide ballot / shuffle scan, one atomicAdd per block and counter).
 //   cell_list[ci] = b * cells + cell     cell_row0[ci] = first row     cell_nv[ci] = n  (float: it multiplies b3's gradient)
 //   row_pt[r] = b * N + point            row_cell[r] = ci              row_cx / row_cy[r] = the cell's centre
+//   row_off[j * row_cap + r], j = 0..2 = (px - cx, py - cy, pz): the three offset inputs of layer 1 for that row
 // counters[0] = live cells, counters[1] = live rows (zeroed by the caller of the kernel).
 __global__ void __launch_bounds__(256) k_bwd_compact(const int32_t *__restrict__ knn, int64_t ncell, int64_t cells, int32_t W,
                                                      int32_t K, int32_t N, float x0, float y0, float dx, float dy,
                                                      int32_t *__restrict__ counters, int32_t *__restrict__ cell_list,
                                                      int32_t *__restrict__ cell_row0, float *__restrict__ cell_nv,
                                                      int32_t *__restrict__ row_pt, int32_t *__restrict__ row_cell,
-                                                     float *__restrict__ row_cx, float *__restrict__ row_cy)
+                                                     float *__restrict__ row_cx, float *__restrict__ row_cy,
+                                                     const float *__restrict__ points, float *__restrict__ row_off,
+                                                     int64_t row_cap)
 {
     __shared__ int32_t warp_cells[8], warp_rows[8], base[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -224,6 +239,10 @@ __global__ void __launch_bounds__(256) k_bwd_compact(const int32_t *__restrict__
         row_cell[r] = ci;
         row_cx[r] = cx;
         row_cy[r] = cy;
+        const float *q = points + ((size_t)b * N + p) * 3;
+        row_off[r] = __fsub_rn(__ldg(q), cx);
+        row_off[row_cap + r] = __fsub_rn(__ldg(q + 1), cy);
+        row_off[2 * row_cap + r] = __ldg(q + 2);
         ++r;
     }
 }
@@ -277,11 +296,11 @@ __global__ void __launch_bounds__(256) k_bwd_h1(const float *__restrict__ T, con
     }
 }
 
-// H2[r, c] = relu(Z[r, c] + b2[c]) (in place on Z);  pooled[ci, c] = sum over the cell's rows
+// H2[r, c] = relu(Z[r, c] + b2[c]) (in place on Z; skipped when `activated`);  pooled[ci, c] = sum over the cell's rows
 __global__ void __launch_bounds__(256) k_bwd_h2_pool(float *__restrict__ Z, const int32_t *__restrict__ cell_row0,
                                                      const float *__restrict__ cell_nv, const float *__restrict__ b2,
                                                      const int32_t *__restrict__ counters, int32_t C,
-                                                     float *__restrict__ pooled)
+                                                     float *__restrict__ pooled, int activated)
 {
     const int64_t total = (int64_t)__ldg(counters) * C;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -291,10 +310,14 @@ __global__ void __launch_bounds__(256) k_bwd_h2_pool(float *__restrict__ Z, cons
         const int32_t nv = (int32_t)__ldg(cell_nv + ci);
         const float bias = __ldg(b2 + c);
         float s = 0.0f;
-        for (int k = 0; k < nv; ++k) {
-            const float h = fmaxf(Z[(r0 + k) * C + c] + bias, 0.0f);
-            Z[(r0 + k) * C + c] = h;
-            s += h;
+        if (activated) {  // the GEMM epilogue already applied bias + ReLU
+            for (int k = 0; k < nv; ++k) s += Z[(r0 + k) * C + c];
+        } else {
+            for (int k = 0; k < nv; ++k) {
+                const float h = fmaxf(Z[(r0 + k) * C + c] + bias, 0.0f);
+                Z[(r0 + k) * C + c] = h;
+                s += h;
+            }
         }
         pooled[t] = s;
     }
@@ -384,13 +407,14 @@ __global__ void __launch_bounds__(256) k_point_gather_bwd(const float *__restric
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct BwdWs {
-    float *H1, *H2, *pooled, *G, *dPooled, *row_cx, *row_cy, *cell_nv, *T, *dT, *W2t;
+    float *H1, *H2, *pooled, *G, *dPooled, *row_cx, *row_cy, *row_off, *cell_nv, *T, *dT, *W2t;
     int32_t *cell_list, *cell_row0, *row_pt, *row_cell, *counters;
+    void *pW2, *pW2t, *pW3t, *pW1t;  // bf16 hi | lo operand images of the weights (tensor-core path)
     size_t bytes;
 };
 
 // sized for the dense upper bound (every slot of every cell holds a neighbour)
-static BwdWs carve(void *base, int32_t B, int32_t N, int32_t C, int64_t cells, int32_t K)
+static BwdWs carve(void *base, int32_t B, int32_t N, int32_t C, int32_t Ci, int64_t cells, int32_t K)
 {
     BwdWs w;
     size_t off = 0;
@@ -407,6 +431,7 @@ static BwdWs carve(void *base, int32_t B, int32_t N, int32_t C, int64_t cells, i
     w.dPooled = (float *)take(ncell * C);
     w.row_cx = (float *)take(rows);
     w.row_cy = (float *)take(rows);
+    w.row_off = (float *)take(3 * rows);
     w.cell_nv = (float *)take(ncell);
     w.T = (float *)take((size_t)B * N * C);
     w.dT = (float *)take((size_t)B * N * C);
@@ -416,6 +441,10 @@ static BwdWs carve(void *base, int32_t B, int32_t N, int32_t C, int64_t cells, i
     w.row_pt = (int32_t *)take(rows);
     w.row_cell = (int32_t *)take(rows);
     w.counters = (int32_t *)take(2);
+    w.pW2 = take(bwd_tc_packed_bytes(C, C) / 4);
+    w.pW2t = take(bwd_tc_packed_bytes(C, C) / 4);
+    w.pW3t = take(bwd_tc_packed_bytes(C, C) / 4);
+    w.pW1t = take(bwd_tc_packed_bytes(Ci, C) / 4);
     w.bytes = off;
     return w;
 }
@@ -440,20 +469,22 @@ int point_mlp1_simt(const float *d_feat, const float *d_points, const int64_t *d
 
 }  // namespace cf
 
-extern "C" size_t cf_fusion_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t H, int32_t W, int32_t K)
+extern "C" size_t cf_fusion_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t Ci, int32_t H, int32_t W, int32_t K)
 {
-    if (B <= 0 || N <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    return cf::carve(nullptr, B, N, C, (int64_t)H * W, K).bytes;
+    if (B <= 0 || N <= 0 || C <= 0 || Ci <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    return cf::carve(nullptr, B, N, C, Ci, (int64_t)H * W, K).bytes;
 }
 
 // Gradients are ACCUMULATED into d_gW1 (C,Ci+3), d_gb1, d_gW2 (C,C), d_gb2, d_gW3, d_gb3 and d_gfeat (B,N,Ci): the
 // caller zero-initialises them (or passes buffers that already hold other scales' contributions).  d bev = d_gout.
+// d_T: the table the forward computed with cf_point_mlp1 (nullptr: it is recomputed here).
+// mode: CF_MODE_FP32_SIMT = every GEMM on CUDA cores (cross-check); otherwise the GEMMs whose operands fit run on tcgen05.
 extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const float *d_points,
                              const int64_t *d_num_points, const int32_t *d_knn_idx, int32_t B, int32_t N, int32_t C,
                              int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
                              const float *d_W1, const float *d_b1, int32_t Ci, const float *d_W2, const float *d_b2,
-                             const float *d_W3, float *d_gW1, float *d_gb1, float *d_gW2, float *d_gb2, float *d_gW3,
-                             float *d_gb3, float *d_gfeat, void *d_workspace, void *stream)
+                             const float *d_W3, const float *d_T, float *d_gW1, float *d_gb1, float *d_gW2, float *d_gb2,
+                             float *d_gW3, float *d_gb3, float *d_gfeat, int32_t mode, void *d_workspace, void *stream)
 {
     using namespace cf;
     CF_TRY(require_sm100());
@@ -462,70 +493,143 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
                CF_ERR_ARG, "cf_fusion_bwd: null pointer");
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && C > 0 && H > 0 && W > 0 && K >= 1 && K <= CF_MAX_K && Ci > 0 && Ci % 4 == 0,
                CF_ERR_ARG, "cf_fusion_bwd: bad extents");
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_FP32_SIMT, CF_ERR_ARG, "cf_fusion_bwd: unknown mode %d",
+               mode);
     CF_REQUIRE(aligned16(d_workspace), CF_ERR_ALIGN, "cf_fusion_bwd: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t cells = (int64_t)H * W, ncell = cells * B, rows = cells * K * B;
     CF_REQUIRE(rows < (int64_t)1 << 31 && (int64_t)B * N < (int64_t)1 << 31, CF_ERR_ARG,
                "cf_fusion_bwd: B*H*W*K and B*N must stay below 2^31");
-    BwdWs w = carve(d_workspace, B, N, C, cells, K);
+    BwdWs w = carve(d_workspace, B, N, C, Ci, cells, K);
     const int32_t ldw1 = Ci + 3;
     const int32_t *n_cells = w.counters, *n_rows = w.counters + 1;
     const unsigned cchunks = (unsigned)((C + 31) / 32), ctiles = (unsigned)((C + 63) / 64);
+    const bool tc = mode != CF_MODE_FP32_SIMT && aligned16(d_gfeat) && aligned16(d_feat) && (!d_T || aligned16(d_T));
+    const bool tc_row_nn = tc && bwd_tc_nn_fits(C, C);    // [rows x C] x [C x C]: the weight image + one A chunk fit up to C = 128
+    const bool tc_row_tn = tc && bwd_tc_tn_fits(C, C);
+    const bool tc_pt_nn = tc && bwd_tc_nn_fits(C, Ci);    // dF = dT W1
+    const bool tc_pt_tn = tc && bwd_tc_tn_fits(C, Ci);    // dW1 | db1 = dT^T [F | P | 1]
+    const bool col2 = tc_row_tn && C + 1 <= 256;          // db2 / db3 ride in the GEMM as an extra column
+    int launches = 0;
 
     // ---- live cells / rows, then the forward intermediates on them ----------------------------------------------------
     CF_TRY(cuda_status(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int32_t), st), "cf_fusion_bwd memset"));
     k_bwd_compact<<<(unsigned)ceil_div64(ncell, 256), 256, 0, st>>>(d_knn_idx, ncell, cells, W, K, N, x0, y0, dx, dy, w.counters,
                                                                    w.cell_list, w.cell_row0, w.cell_nv, w.row_pt, w.row_cell,
-                                                                   w.row_cx, w.row_cy);
-    CF_TRY(point_mlp1_simt(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, w.T, st));
-    k_bwd_h1<<<blocks_for(rows, 8), 256, 0, st>>>(w.T, w.row_pt, w.row_cx, w.row_cy, w.counters, C, d_W1, Ci, w.H1);
-    k_transpose_sq_b<<<(C * C + 255) / 256, 256, 0, st>>>(d_W2, C, w.W2t);
-    // Z2 = H1 W2^T  (as  H1 [rows x C] * W2t [C x C])
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H1, C, w.W2t, C, w.H2, C, rows, C, C, 0, nullptr,
-                                                                            0, n_rows);
-    k_bwd_h2_pool<<<blocks_for(ncell * C, 256), 256, 0, st>>>(w.H2, w.cell_row0, w.cell_nv, d_b2, w.counters, C, w.pooled);
+                                                                   w.row_cx, w.row_cy, d_points, w.row_off, rows);
+    const float *T = d_T;
+    if (!T) {
+        CF_TRY(point_mlp1_simt(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, w.T, st));
+        T = w.T;
+    }
+    k_bwd_h1<<<blocks_for(rows, 8), 256, 0, st>>>(T, w.row_pt, w.row_cx, w.row_cy, w.counters, C, d_W1, Ci, w.H1);
+    launches += 2;
+    if (tc_row_nn) {
+        CF_TRY(bwd_tc_pack(d_W2, C, C, C, 0, w.pW2, st));
+        CF_TRY(bwd_tc_pack(d_W2, C, C, C, 1, w.pW2t, st));
+        CF_TRY(bwd_tc_pack(d_W3, C, C, C, 1, w.pW3t, st));
+        // H2 = relu(H1 W2^T + b2)
+        CF_TRY(bwd_tc_gemm_nn(w.H1, C, rows, n_rows, C, C, w.pW2, w.H2, C, EPI_BIAS_RELU, d_b2, 0, st));
+    } else {
+        k_transpose_sq_b<<<(C * C + 255) / 256, 256, 0, st>>>(d_W2, C, w.W2t);
+        // Z2 = H1 W2^T  (as  H1 [rows x C] * W2t [C x C])
+        k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H1, C, w.W2t, C, w.H2, C, rows, C, C, 0,
+                                                                                nullptr, 0, n_rows);
+        launches += 2;
+    }
+    k_bwd_h2_pool<<<blocks_for(ncell * C, 256), 256, 0, st>>>(w.H2, w.cell_row0, w.cell_nv, d_b2, w.counters, C, w.pooled,
+                                                              tc_row_nn ? 1 : 0);
 
     // ---- layer 3 ------------------------------------------------------------------------------------------------------
     k_bwd_gather_g<<<dim3((unsigned)ceil_div64(ncell, 32), cchunks), 256, 0, st>>>(d_gout, C, cells, w.cell_list, w.counters,
                                                                                   w.G);
-    const int64_t split3 = std::max<int64_t>(256, ceil_div64(ncell, 1184));
-    k_sgemm_tn<<<dim3(ctiles, ctiles, (unsigned)ceil_div64(ncell, split3)), 256, 0, st>>>(w.G, C, w.pooled, C, d_gW3, C, ncell, C,
-                                                                                         C, split3, n_cells);
-    k_colsum<<<dim3((unsigned)ceil_div64(ncell, 1024), cchunks), 256, 0, st>>>(w.G, C, ncell, C, w.cell_nv, 1.0f, d_gb3, 1,
-                                                                              n_cells);
+    launches += 2;
+    if (tc_row_tn) {
+        CF_TRY(bwd_tc_gemm_tn(w.G, C, C, w.pooled, C, C, nullptr, 0, 0, 0, w.cell_nv, ncell, n_cells, d_gW3, C,
+                              col2 ? d_gb3 : nullptr, st));
+    } else {
+        const int64_t split3 = std::max<int64_t>(256, ceil_div64(ncell, 1184));
+        k_sgemm_tn<<<dim3(ctiles, ctiles, (unsigned)ceil_div64(ncell, split3)), 256, 0, st>>>(w.G, C, w.pooled, C, d_gW3, C, ncell,
+                                                                                             C, C, split3, n_cells);
+        ++launches;
+    }
+    if (!(tc_row_tn && col2)) {
+        k_colsum<<<dim3((unsigned)ceil_div64(ncell, 1024), cchunks), 256, 0, st>>>(w.G, C, ncell, C, w.cell_nv, 1.0f, d_gb3, 1,
+                                                                                  n_cells);
+        ++launches;
+    }
     // dPooled = G W3   (W3 is (out, in) row-major: exactly the [K=out x N=in] operand)
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(ncell, 64), ctiles), 256, 0, st>>>(w.G, C, d_W3, C, w.dPooled, C, ncell, C, C, 0,
-                                                                             nullptr, 0, n_cells);
+    if (tc_row_nn) {
+        CF_TRY(bwd_tc_gemm_nn(w.G, C, ncell, n_cells, C, C, w.pW3t, w.dPooled, C, EPI_STORE, nullptr, 0, st));
+    } else {
+        k_sgemm_nn<<<dim3((unsigned)ceil_div64(ncell, 64), ctiles), 256, 0, st>>>(w.G, C, d_W3, C, w.dPooled, C, ncell, C, C, 0,
+                                                                                 nullptr, 0, n_cells);
+        ++launches;
+    }
 
     // ---- layer 2 ------------------------------------------------------------------------------------------------------
     k_bwd_dz2<<<blocks_for(rows * C, 256), 256, 0, st>>>(w.H2, w.dPooled, w.row_cell, w.counters, C);  // H2 now holds dZ2
-    const int64_t split2 = std::max<int64_t>(256, ceil_div64(rows, 1184));
-    k_sgemm_tn<<<dim3(ctiles, ctiles, (unsigned)ceil_div64(rows, split2)), 256, 0, st>>>(w.H2, C, w.H1, C, d_gW2, C, rows, C, C,
-                                                                                        split2, n_rows);
-    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H2, C, rows, C, nullptr, 1.0f, d_gb2, 1, n_rows);
+    ++launches;
+    if (tc_row_tn) {
+        CF_TRY(bwd_tc_gemm_tn(w.H2, C, C, w.H1, C, C, nullptr, 0, 0, 0, nullptr, rows, n_rows, d_gW2, C,
+                              col2 ? d_gb2 : nullptr, st));
+    } else {
+        const int64_t split2 = std::max<int64_t>(256, ceil_div64(rows, 1184));
+        k_sgemm_tn<<<dim3(ctiles, ctiles, (unsigned)ceil_div64(rows, split2)), 256, 0, st>>>(w.H2, C, w.H1, C, d_gW2, C, rows, C,
+                                                                                            C, split2, n_rows);
+        ++launches;
+    }
+    if (!(tc_row_tn && col2)) {
+        k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H2, C, rows, C, nullptr, 1.0f, d_gb2, 1,
+                                                                                 n_rows);
+        ++launches;
+    }
     // dA = (dZ2 W2) * [H1 > 0]   written over H1 (the mask is read before the overwrite, element by element)
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H2, C, d_W2, C, w.H1, C, rows, C, C, 0, w.H1, C,
-                                                                            n_rows);
+    if (tc_row_nn) {
+        CF_TRY(bwd_tc_gemm_nn(w.H2, C, rows, n_rows, C, C, w.pW2t, w.H1, C, EPI_MASK, w.H1, C, st));
+    } else {
+        k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H2, C, d_W2, C, w.H1, C, rows, C, C, 0, w.H1,
+                                                                                C, n_rows);
+        ++launches;
+    }
 
-    // ---- layer 1: cell-side offset columns, scatter to points, point-side GEMMs -----------------------------------------
-    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H1, C, rows, C, w.row_cx, -1.0f, d_gW1 + Ci, ldw1,
-                                                                             n_rows);
-    k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H1, C, rows, C, w.row_cy, -1.0f, d_gW1 + Ci + 1,
-                                                                             ldw1, n_rows);
+    // ---- layer 1: offset columns from the rows, scatter to points, point-side GEMMs ----------------------------------------
+    // dW1[:, Ci + j] = sum_r dA_r * off_j(r) with off = (px - cx, py - cy, pz) of the row: summed as they entered the
+    // forward (small numbers), not as the difference of two large point-side and cell-side sums
+    if (tc_row_tn) {
+        CF_TRY(bwd_tc_gemm_tn(w.H1, C, C, nullptr, 0, 0, w.row_off, 1, rows, 3, nullptr, rows, n_rows, d_gW1 + Ci, ldw1, nullptr,
+                              st));
+    } else {
+        for (int j = 0; j < 3; ++j)
+            k_colsum<<<dim3((unsigned)ceil_div64(rows, 1024), cchunks), 256, 0, st>>>(w.H1, C, rows, C, w.row_off + j * rows, 1.0f,
+                                                                                     d_gW1 + Ci + j, ldw1, n_rows);
+        launches += 3;
+    }
     CF_TRY(cuda_status(cudaMemsetAsync(w.dT, 0, (size_t)B * N * C * sizeof(float), st), "cf_fusion_bwd memset"));
     k_bwd_scatter<<<blocks_for(rows, 8), 256, 0, st>>>(w.H1, w.row_pt, w.counters, C, w.dT);
+    ++launches;
     const int64_t pts = (int64_t)B * N;
-    const int64_t splitp = std::max<int64_t>(512, ceil_div64(pts, 148));
-    // feat / points rows beyond num_points are never referenced by knn, so their dT rows are zero
-    k_sgemm_tn<<<dim3(ctiles, (unsigned)((Ci + 63) / 64), (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(
-        w.dT, C, d_feat, Ci, d_gW1, ldw1, pts, C, Ci, splitp, nullptr);
-    k_sgemm_tn<<<dim3(ctiles, 1, (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(w.dT, C, d_points, 3, d_gW1 + Ci, ldw1, pts,
-                                                                                  C, 3, splitp, nullptr);
-    k_colsum<<<dim3((unsigned)ceil_div64(pts, 1024), cchunks), 256, 0, st>>>(w.dT, C, pts, C, nullptr, 1.0f, d_gb1, 1, nullptr);
+    // feat rows beyond num_points are zero and never referenced by knn, so their dT rows are zero as well
+    if (tc_pt_tn) {
+        CF_TRY(bwd_tc_gemm_tn(w.dT, C, C, d_feat, Ci, Ci, nullptr, 0, 0, 0, nullptr, pts, nullptr, d_gW1, ldw1, d_gb1, st));
+    } else {
+        const int64_t splitp = std::max<int64_t>(512, ceil_div64(pts, 148));
+        k_sgemm_tn<<<dim3(ctiles, (unsigned)((Ci + 63) / 64), (unsigned)ceil_div64(pts, splitp)), 256, 0, st>>>(
+            w.dT, C, d_feat, Ci, d_gW1, ldw1, pts, C, Ci, splitp, nullptr);
+        k_colsum<<<dim3((unsigned)ceil_div64(pts, 1024), cchunks), 256, 0, st>>>(w.dT, C, pts, C, nullptr, 1.0f, d_gb1, 1,
+                                                                                nullptr);
+        launches += 2;
+    }
     // dF += dT W1[:, :Ci]
-    k_sgemm_nn<<<dim3((unsigned)ceil_div64(pts, 64), (unsigned)((Ci + 63) / 64)), 256, 0, st>>>(
-        w.dT, C, d_W1, ldw1, d_gfeat, Ci, pts, Ci, C, 1, nullptr, 0, nullptr);
-    count_launches(19);
+    if (tc_pt_nn) {
+        CF_TRY(bwd_tc_pack(d_W1, ldw1, Ci, C, 1, w.pW1t, st));
+        CF_TRY(bwd_tc_gemm_nn(w.dT, C, pts, nullptr, C, Ci, w.pW1t, d_gfeat, Ci, EPI_ACCUM, nullptr, 0, st));
+    } else {
+        k_sgemm_nn<<<dim3((unsigned)ceil_div64(pts, 64), (unsigned)((Ci + 63) / 64)), 256, 0, st>>>(
+            w.dT, C, d_W1, ldw1, d_gfeat, Ci, pts, Ci, C, 1, nullptr, 0, nullptr);
+        ++launches;
+    }
+    count_launches(launches);
     return launch_status("cf_fusion_bwd");
 }
 

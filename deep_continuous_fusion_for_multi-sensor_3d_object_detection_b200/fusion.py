@@ -261,15 +261,16 @@ class _FusionFunction(torch.autograd.Function):
             p1 = packed.w1(w1, mode) if packed is not None else None
             table = ops.point_mlp1(feat, points, num_points, w1, b1, mode=mode, packed=p1)
         out, _ = ops.fusion_fwd(bev, table, knn_idx, geom, w1, w2, b2, w3, b3, mode=mode, packed=p23, out=out)
-        ctx.save_for_backward(feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3)
+        # the table is kept for the backward (B*N*C floats: far smaller than the activations autograd keeps for one conv)
+        ctx.save_for_backward(feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3, table)
         ctx.geom, ctx.mode = geom, mode
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3 = ctx.saved_tensors
+        feat, points, num_points, knn_idx, w1, b1, w2, b2, w3, b3, table = ctx.saved_tensors
         gw1, gb1, gw2, gb2, gw3, gb3, gfeat = ops.fusion_bwd(grad_out, feat, points, num_points, knn_idx, ctx.geom, w1, b1,
-                                                             w2, b2, w3)
+                                                             w2, b2, w3, table=table, mode=ctx.mode)
         # d out / d bev is the identity
         return grad_out, gfeat, None, None, None, None, None, gw1, gb1, gw2, gb2, gw3, gb3, None, None, None
 

@@ -286,8 +286,11 @@ def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None,
     return out, workspace
 
 
-def fusion_bwd(grad_out, feat, points, num_points, knn_idx, geom, W1, b1, W2, b2, W3, grad_feat=None):
-    """K-4b.  Returns (gW1, gb1, gW2, gb2, gW3, gb3, gfeat); d bev is grad_out itself."""
+def fusion_bwd(grad_out, feat, points, num_points, knn_idx, geom, W1, b1, W2, b2, W3, grad_feat=None, table=None,
+               mode="fp32"):
+    """K-4b.  Returns (gW1, gb1, gW2, gb2, gW3, gb3, gfeat); d bev is grad_out itself.
+    `table`: the forward's point_mlp1 output (B,N,C) if it was kept (else it is recomputed); `mode` "simt" keeps every
+    GEMM on CUDA cores, any other mode runs them on tcgen05 with fp32-accurate split operands."""
     lib = load()
     grad_out = _contig(grad_out, "grad_out", torch.float32, 4)
     feat = _contig(feat, "feat", torch.float32, 3)
@@ -302,11 +305,15 @@ def fusion_bwd(grad_out, feat, points, num_points, knn_idx, geom, W1, b1, W2, b2
     gW2, gb2 = torch.zeros_like(W2), torch.zeros_like(b2)
     gW3, gb3 = torch.zeros_like(W3), torch.zeros((Cc,), dtype=torch.float32, device=dev)
     gfeat = torch.zeros_like(feat) if grad_feat is None else grad_feat
-    ws = torch.empty((max(lib.cf_fusion_bwd_workspace_bytes(B, N, Cc, H, W, K), 16),), dtype=torch.uint8, device=dev)
+    if table is not None:
+        table = _contig(table, "table", torch.float32, 3)
+        if tuple(table.shape) != (B, N, Cc):
+            raise ValueError("fusion_bwd: table must be (B, N, C)")
+    ws = torch.empty((max(lib.cf_fusion_bwd_workspace_bytes(B, N, Cc, Ci, H, W, K), 16),), dtype=torch.uint8, device=dev)
     x0, y0, dx, dy = [float(g) for g in geom]
     check(lib.cf_fusion_bwd(ptr(grad_out), ptr(feat), ptr(points), ptr(num_points), ptr(knn_idx), B, N, Cc, H, W, K, x0, y0,
-                            dx, dy, ptr(W1), ptr(b1), Ci, ptr(W2), ptr(b2), ptr(W3), ptr(gW1), ptr(gb1), ptr(gW2),
-                            ptr(gb2), ptr(gW3), ptr(gb3), ptr(gfeat), ptr(ws), stream_ptr()), "cf_fusion_bwd")
+                            dx, dy, ptr(W1), ptr(b1), Ci, ptr(W2), ptr(b2), ptr(W3), ptr(table), ptr(gW1), ptr(gb1), ptr(gW2),
+                            ptr(gb2), ptr(gW3), ptr(gb3), ptr(gfeat), (_lib.MODES[mode] if isinstance(mode, str) else int(mode)), ptr(ws), stream_ptr()), "cf_fusion_bwd")
     return gW1, gb1, gW2, gb2, gW3, gb3, gfeat
 
 
@@ -407,3 +414,31 @@ def debug_umma_gemm(A, Bm, split=False):
     check(lib.cf_debug_umma_gemm(ptr(A), ptr(Bm), Bm.shape[0], A.shape[1], int(bool(split)), ptr(D), stream_ptr()),
           "cf_debug_umma_gemm")
     return D
+
+
+def debug_bwd_gemm_nn(X, Wm, transpose=False, epi=0, aux=None, out=None, row_count=None):
+    """Self-test of the NN GEMM of the backward: epi(X @ B.T), B = Wm (N,Kd) or Wm.T with Wm (Kd,N)."""
+    lib = load()
+    X = _contig(X, "X", torch.float32, 2)
+    Wm = _contig(Wm, "W", torch.float32, 2)
+    R, Kd = X.shape
+    N = Wm.shape[1] if transpose else Wm.shape[0]
+    out = torch.zeros((R, N), dtype=torch.float32, device=X.device) if out is None else out
+    packed = torch.empty((lib.cf_debug_bwd_packed_bytes(N, Kd),), dtype=torch.uint8, device=X.device)
+    check(lib.cf_debug_bwd_gemm_nn(ptr(X), R, ptr(row_count), Kd, N, ptr(Wm), int(bool(transpose)), ptr(out), int(epi),
+                                   ptr(aux), ptr(packed), stream_ptr()), "cf_debug_bwd_gemm_nn")
+    return out
+
+
+def debug_bwd_gemm_tn(X, Y=None, Y2=None, wcol=None, bias=False, row_count=None):
+    """Self-test of the TN GEMM of the backward: (X.T @ [Y | Y2], X.T @ (wcol or 1))."""
+    lib = load()
+    X = _contig(X, "X", torch.float32, 2)
+    R, M = X.shape
+    N = 0 if Y is None else Y.shape[1]
+    n2 = 0 if Y2 is None else Y2.shape[1]
+    dW = torch.zeros((M, N + n2), dtype=torch.float32, device=X.device)
+    db = torch.zeros((M,), dtype=torch.float32, device=X.device) if bias else None
+    check(lib.cf_debug_bwd_gemm_tn(ptr(X), M, ptr(Y), N, ptr(Y2), n2, ptr(wcol), R, ptr(row_count), ptr(dW), ptr(db),
+                                   stream_ptr()), "cf_debug_bwd_gemm_tn")
+    return dW, db

@@ -30,7 +30,7 @@ extern "C" {
 #define CF_API
 #endif
 
-#define CF_ABI_VERSION 1
+#define CF_ABI_VERSION 2
 
 #define CF_OK 0
 #define CF_ERR_ARG (-1)         /* bad shape / null pointer / unsupported size */
@@ -148,18 +148,23 @@ CF_API int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t *d_
  * K-4b backward of cf_point_mlp1 + cf_fusion_fwd for one scale (training only).  d_gout = dL/d out (B,C,H,W);
  * dL/d bev is d_gout itself.  Gradients are ACCUMULATED into d_gW1 (C,Ci+3), d_gb1 (C), d_gW2 (C,C), d_gb2,
  * d_gW3, d_gb3 and d_gfeat (B,N,Ci) -- zero them first (d_gfeat collects every scale's contribution).
- * The forward saves only indices, inputs and weights; H1/H2/pooled are recomputed into the workspace
- * (cf_fusion_bwd_workspace_bytes).  fp32 on CUDA cores; reductions use atomics (reproducible to rounding).
+ * The forward saves only indices, inputs and weights (and, optionally, its table: d_T = the output of
+ * cf_point_mlp1, NULL = recompute it); H1/H2/pooled are recomputed into the workspace
+ * (cf_fusion_bwd_workspace_bytes), for the (cell, k) slots that hold a neighbour only.
+ * mode CF_MODE_FP32 / CF_MODE_BF16: the GEMMs run on tcgen05 (fp32 operands split into bf16 hi + lo, three MMAs,
+ * fp32 accumulate -- gradients are fp32-accurate in both modes); CF_MODE_FP32_SIMT, or shapes without a
+ * tensor-core instantiation: FFMA kernels.  Reductions over rows use atomics (reproducible to rounding).
  * cf_point_gather_bwd is the adjoint of cf_point_gather: d_gimg (+)= bilinear scatter of d_gfeat; d_gimg has the
  * camera map's logical shape and the given element strides.
  * ------------------------------------------------------------------------------------------- */
-CF_API size_t cf_fusion_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t H, int32_t W, int32_t K);
+CF_API size_t cf_fusion_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t Ci, int32_t H, int32_t W,
+                                            int32_t K);
 CF_API int cf_fusion_bwd(const float *d_gout, const float *d_feat, const float *d_points,
                   const int64_t *d_num_points, const int32_t *d_knn_idx, int32_t B, int32_t N, int32_t C,
                   int32_t H, int32_t W, int32_t K, float x0, float y0, float dx, float dy,
                   const float *d_W1, const float *d_b1, int32_t Ci, const float *d_W2, const float *d_b2,
-                  const float *d_W3, float *d_gW1, float *d_gb1, float *d_gW2, float *d_gb2, float *d_gW3,
-                  float *d_gb3, float *d_gfeat, void *d_workspace, void *stream);
+                  const float *d_W3, const float *d_T, float *d_gW1, float *d_gb1, float *d_gW2, float *d_gb2,
+                  float *d_gW3, float *d_gb3, float *d_gfeat, int32_t mode, void *d_workspace, void *stream);
 CF_API int cf_point_gather_bwd(const float *d_gfeat, float *d_gimg, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
                         int32_t B, int32_t Ci, int32_t Hf, int32_t Wf, const float *d_points,
                         const float *d_uv, const float *h_calib, const int64_t *d_num_points, int32_t N,
@@ -226,6 +231,20 @@ CF_API int cf_box_iou(const float *d_boxes_a, int32_t na, const float *d_boxes_b
  * ------------------------------------------------------------------------------------------- */
 CF_API int cf_debug_umma_gemm(const float *d_A, const float *d_B, int32_t N, int32_t K, int32_t split, float *d_D,
                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-tests of the two tcgen05 GEMM shapes behind cf_fusion_bwd (fp32 operands split into bf16 hi + lo):
+ *   nn: Out (R,N) = epi( X (R,Kd) * B^T ),  B = W (N,Kd) [transpose 0] or W^T with W (Kd,N) [transpose 1];
+ *       epi 0 store, 1 accumulate, 2 relu(. + aux[N]), 3 zero where aux (R,N) <= 0.  Kd, N % 32 == 0.
+ *   tn: dW (M, N+n2) += X (R,M)^T * [Y (R,N) | Y2 (R,n2)],  db (M) += X^T * (wcol or 1);  M, N % 32 == 0, n2 <= 15.
+ *   d_R (device int32, may be NULL) clamps R without a host synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+CF_API size_t cf_debug_bwd_packed_bytes(int32_t N, int32_t Kd);
+CF_API int cf_debug_bwd_gemm_nn(const float *d_X, int64_t R, const int32_t *d_R, int32_t Kd, int32_t N, const float *d_W,
+                         int32_t transpose, float *d_Out, int32_t epi, const float *d_aux, void *d_packed,
+                         void *stream);
+CF_API int cf_debug_bwd_gemm_tn(const float *d_X, int32_t M, const float *d_Y, int32_t N, const float *d_Y2, int32_t n2,
+                         const float *d_wcol, int64_t R, const int32_t *d_R, float *d_dW, float *d_db, void *stream);
 
 #ifdef __cplusplus
 }

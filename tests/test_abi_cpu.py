@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(dcf):
 
 def test_abi_version_and_error_channel(dcf):
     lib = dcf.load()
-    assert lib.cf_abi_version() == 1
+    assert lib.cf_abi_version() == 2
     assert isinstance(lib.cf_last_error(), bytes)
     assert lib.cf_fusion_workspace_bytes(128, 0, 2, 96, 64) >= 2 * 2 * 128 * 128 * 2 + 2 * 96 * 64 * 4
     assert lib.cf_nms_workspace_bytes(2, 2048) >= 2 * 2048 * 32 * 8

@@ -1,7 +1,12 @@
 """GPU: K-4b.  Gradients of the fused layer (w.r.t. the BEV map, the camera feature map and all six MLP
 parameters) against PyTorch autograd on a float64 restatement of the same layer (grid_sample gather, gathered rows,
-three Linear layers, masked sum-pool).  Tolerance 2e-3 relative L2 (2e-2 max norm) per gradient: the forward runs the fp32
-tensor-core mode, the backward fp32 CUDA cores with atomics."""
+three Linear layers, masked sum-pool).  Mode "simt": every GEMM of the backward on fp32 CUDA cores, tolerance 2e-3 relative L2
+(2e-2 max norm) per gradient.  Mode "fp32": the GEMMs on tcgen05 with split-bf16 operands (~1.5e-5 relative per product; the
+GEMM kernels themselves are held to 1e-4 in test_gpu_bwd_gemm.py), tolerance 5e-3 / 5e-2.  The tolerances are this wide
+because of the ReLU kinks, not of the arithmetic: a gradient is either within ~1e-6 (simt) / ~1e-5 (fp32) of the float64
+reference, or a pre-activation that is zero to rounding switches side and ONE full-size term of the sum changes (~1e-3
+of the tensor's norm at these sizes); how often that happens is proportional to the rounding error of the recomputed
+pre-activations, so the tensor-core mode sees a few more of them."""
 import numpy as np
 import pytest
 import torch
@@ -76,19 +81,31 @@ def test_backward_matches_autograd(dcf, mode):
         ref_params.append(w64); ref_bevs.append(b64)
     ref_loss.backward()
 
-    def close(a, b, name, tol=2e-3):
+    report, bad = [], []
+
+    base_tol = 2e-3 if mode == "simt" else 5e-3
+
+    def close(a, b, name, tol=None):
+        tol = base_tol if tol is None else tol
         # relative L2 error, plus a looser max-norm bound: a ReLU whose pre-activation is within fp32 rounding of zero
         # can switch between the fp32 kernels and the fp64 reference, which perturbs a few entries, not the bulk
         l2 = (a.double() - b).norm().item() / max(b.norm().item(), 1e-12)
         mx = (a.double() - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
-        assert l2 < tol and mx < 10 * tol, f"{name}: rel L2 err {l2:.3e}, rel max err {mx:.3e}"
+        report.append(f"{name}: rel L2 err {l2:.3e}, rel max err {mx:.3e}")
+        if not (l2 < tol and mx < 10 * tol):
+            bad.append(report[-1])
 
     close(img.grad, img64.grad, "d img_feat")
     for g, (layer, w64, bev, b64) in enumerate(zip(layers, ref_params, bevs, ref_bevs)):
         close(bev.grad, b64.grad, f"scale {g} d bev", 1e-6)
-        for name, p_, r_ in zip(["W1", "b1", "W2", "b2", "W3", "b3"], (layer.fc1.weight, layer.fc1.bias, layer.fc2.weight,
-                                                                        layer.fc2.bias, layer.fc3.weight, layer.fc3.bias), w64):
+        ci = layer.c_img
+        close(layer.fc1.weight.grad[:, :ci], w64[0].grad[:, :ci], f"scale {g} d W1[:, image]")
+        close(layer.fc1.weight.grad[:, ci:], w64[0].grad[:, ci:], f"scale {g} d W1[:, offset]")
+        for name, p_, r_ in zip(["b1", "W2", "b2", "W3", "b3"], (layer.fc1.bias, layer.fc2.weight, layer.fc2.bias,
+                                                                  layer.fc3.weight, layer.fc3.bias), w64[1:]):
             close(p_.grad, r_.grad, f"scale {g} d {name}")
+    print("\n".join(report))
+    assert not bad, "\n".join(["gradients outside the tolerance:"] + bad + ["all:"] + report)
 
 
 def test_training_step_through_the_dropin_model(dcf):

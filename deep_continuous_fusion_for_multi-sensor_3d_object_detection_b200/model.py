@@ -115,9 +115,14 @@ class OffsettoBbox(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.anchor_bbox_feature = AnchorBoundingBoxFeature(config)
+        self._anchors = {}   # device -> (1,14,fh,fw): the anchors are constants of the config; the reference rebuilds
+                             # them on the CPU and copies them every forward (model.py:125), which a CUDA-graph
+                             # capture of the step cannot contain
 
     def forward(self, x):
-        anc = self.anchor_bbox_feature().to(x.device).unsqueeze(0)
+        anc = self._anchors.get(x.device)
+        if anc is None:
+            anc = self._anchors[x.device] = self.anchor_bbox_feature().to(x.device).unsqueeze(0)
         outs = []
         for a in (0, 7):
             diag = torch.sqrt(anc[:, a + 3:a + 4] ** 2 + anc[:, a + 4:a + 5] ** 2)

@@ -9,6 +9,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -23,6 +24,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--no-fusion", action="store_true", help="LiDAR-only model (the reference as it is) for comparison")
+    ap.add_argument("--graph", action="store_true", help="capture forward + backward + Adam as ONE CUDA graph and replay it "
+                    "(single process only): the step time without the host's launch overhead")
     a = ap.parse_args()
     rank, world, local = dcf.dist_util.env_rank_world()
     torch.cuda.set_device(local)
@@ -33,13 +36,13 @@ def main():
     model = dcf.ObjectDetection_DCF(cfg).to(dev).eval()      # BatchNorm in eval mode, as in the reference (test.py:37)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=a.graph)
     wl = dcf.synthetic.make_workload(dict(dcf.synthetic.workload("yaml"), batch=a.batch), seed=200 + rank)
     to = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     x_lidar = torch.rand(a.batch, 32, 384, 256, device=dev)
     x_image = torch.randint(0, 255, (a.batch, 3, 480, 640), device=dev, dtype=torch.uint8)
     target = torch.randn(a.batch, 32, 96, 64, device=dev)
-    extra = {} if a.no_fusion else dict(pointcloud_raw=to(wl["points"]), num_points_raw=torch.from_numpy(wl["num_points"]),
+    extra = {} if a.no_fusion else dict(pointcloud_raw=to(wl["points"]), num_points_raw=to(wl["num_points"]),
                                         projected_loc_uv=to(wl["uv"]))
 
     def step():
@@ -50,21 +53,46 @@ def main():
         opt.step()
         return loss
 
+    if a.graph:
+        if world > 1:
+            raise SystemExit("--graph is a single-process measurement")
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            pred = model(x_lidar, x_image, **extra)
+            static_loss = F.mse_loss(pred[:, :18], target[:, :18])
+            static_loss.backward()
+            opt.step()
+
+        def step():  # noqa: F811  (gradients are overwritten in place by the replay, nothing to zero)
+            graph.replay()
+            return static_loss
     for _ in range(3):
         step()
     dcf.dist_util.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(a.steps):
         loss = step()
     e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / a.steps      # time the host needs to ENQUEUE a step (no synchronisation)
     dcf.dist_util.barrier()
     torch.cuda.synchronize()
     ms = dcf.dist_util.max_over_ranks([e0.elapsed_time(e1) / a.steps], device=dev)[0]
     if rank == 0:
         print(json.dumps({"what": "train step (fwd + bwd + Adam), ObjectDetection_DCF, YAML grid 384x256",
-                          "fusion": not a.no_fusion, "batch_per_gpu": a.batch, "n_gpus": world, "ms_per_step": round(ms, 3),
+                          "fusion": not a.no_fusion, "launch": "cuda_graph_replay" if a.graph else "eager",
+                          "batch_per_gpu": a.batch, "n_gpus": world, "ms_per_step": round(ms, 3),
+                          "host_enqueue_ms_per_step": round(host_ms, 3),
                           "frames_per_sec": round(a.batch * world / ms * 1e3, 1), "loss": float(loss)}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -19,7 +19,7 @@ namespace cf {
 namespace {
 
 constexpr int kRows = 128;     // UMMA M
-constexpr int kNT = 256;       // threads per CTA (8 warps: two per TMEM lane quarter)
+constexpr int kNT = 512;       // threads per CTA (16 warps, four per TMEM lane quarter: the kernels live on loads in flight)
 constexpr int kTnKC = 64;      // rows of X / Y per pipeline stage of the TN kernel
 
 __host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
@@ -103,23 +103,34 @@ __global__ void __launch_bounds__(kNT) k_bwd_gemm_nn_tc(const NnParams p)
         for (int ch = 0; ch < chunks; ++ch) {
             // a warp takes one 8-row group x 4 k-units per step: lane (r8 = lane % 8, u = lane / 8) reads 32 bytes of its row
             const float *xb = p.X + r0 * p.ldx + ch * KC;
-            for (int item = warp; item < 16 * (kc_units / 4); item += kNT / 32) {
-                const int rg = item / (kc_units / 4), uq = item - rg * (kc_units / 4);
-                const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
-                float v[8];
-                if (r0 + r < R) {
-                    const float4 *src = reinterpret_cast<const float4 *>(xb + (int64_t)r * p.ldx + ku * 8);
-                    const float4 t0 = src[0], t1 = src[1];
-                    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-                } else {
+            const int n_items = 16 * (kc_units / 4);
+            for (int item = warp; item < n_items; item += 2 * (kNT / 32)) {  // two items per warp in flight
+                float v[2][8];
+                uint32_t off[2];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+                for (int u = 0; u < 2; ++u) {
+                    const int it = item + u * (kNT / 32);
+                    const int rg = it / (kc_units / 4), uq = it - rg * (kc_units / 4);
+                    const int r = rg * 8 + (lane & 7), ku = uq * 4 + (lane >> 3);
+                    off[u] = tc::unit_offset(r, ku, kc_units);
+                    if (it < n_items && r0 + r < R) {
+                        const float4 *src = reinterpret_cast<const float4 *>(xb + (int64_t)r * p.ldx + ku * 8);
+                        const float4 t0 = src[0], t1 = src[1];
+                        v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t0.z; v[u][3] = t0.w;
+                        v[u][4] = t1.x; v[u][5] = t1.y; v[u][6] = t1.z; v[u][7] = t1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[u][i] = 0.0f;
+                    }
                 }
-                uint4 hi, lo;
-                tc::split_bf16x8(v, hi, lo, true);
-                const uint32_t off = tc::unit_offset(r, ku, kc_units);
-                *reinterpret_cast<uint4 *>(sA + off) = hi;
-                *reinterpret_cast<uint4 *>(sA + a_split + off) = lo;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (item + u * (kNT / 32) >= n_items) break;
+                    uint4 hi, lo;
+                    tc::split_bf16x8(v[u], hi, lo, true);
+                    *reinterpret_cast<uint4 *>(sA + off[u]) = hi;
+                    *reinterpret_cast<uint4 *>(sA + a_split + off[u]) = lo;
+                }
             }
             tc::fence_proxy_async();
             tc::fence_before_sync();
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(kNT) k_bwd_gemm_nn_tc(const NnParams p)
         const bool live = r < R;
         __syncwarp();
 #pragma unroll 1
-        for (int cc = grp; cc < N / 32; cc += 2) {
+        for (int cc = grp; cc < N / 32; cc += kNT / kRows) {
             float z[32];
             tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
             if (live) {
@@ -256,41 +267,52 @@ __global__ void __launch_bounds__(kNT) k_bwd_gemm_tn_tc(const TnParams p)
         }
         uint8_t *sA = smem + s * stage_bytes, *sB = sA + 2 * a_split;
         const int64_t r0 = c * kTnKC;
-        for (int item = warp; item < items_a + items_b + items_e; item += kNT / 32) {
-            float v[8];
-            uint8_t *dst;
-            uint32_t split;
-            if (item < items_a + items_b) {
-                const bool isa = item < items_a;
-                const int it = isa ? item : item - items_a;
-                const int cb = it / kc_units, ku = it - cb * kc_units;
-                const int col = cb * 32 + lane;
-                const float *src = isa ? p.X + (r0 + ku * 8) * p.ldx + m0 + col : p.Y + (r0 + ku * 8) * p.ldy + col;
-                const int64_t ld = isa ? p.ldx : p.ldy;
+        const int n_items = items_a + items_b + items_e;
+        for (int item = warp; item < n_items; item += 2 * (kNT / 32)) {  // two items per warp in flight
+            float v[2][8];
+            uint8_t *dst[2];
+            uint32_t split[2];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (r0 + ku * 8 + j < R) ? __ldg(src + j * ld) : 0.0f;
-                dst = (isa ? sA : sB) + tc::unit_offset(col, ku, kc_units);
-                split = isa ? a_split : b_split;
-            } else {
-                if (lane >= n_extra) continue;
-                const int ku = item - items_a - items_b;
+            for (int u = 0; u < 2; ++u) {
+                const int it0 = item + u * (kNT / 32);
+                dst[u] = nullptr;
+                if (it0 >= n_items) continue;
+                if (it0 < items_a + items_b) {
+                    const bool isa = it0 < items_a;
+                    const int it = isa ? it0 : it0 - items_a;
+                    const int cb = it / kc_units, ku = it - cb * kc_units;
+                    const int col = cb * 32 + lane;
+                    const float *src = isa ? p.X + (r0 + ku * 8) * p.ldx + m0 + col : p.Y + (r0 + ku * 8) * p.ldy + col;
+                    const int64_t ld = isa ? p.ldx : p.ldy;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int64_t r = r0 + ku * 8 + j;
-                    float x = 0.0f;
-                    if (r < R) {
-                        if (lane < p.n2) x = __ldg(p.Y2 + r * p.rs2 + lane * p.cs2);
-                        else if (lane == p.n2 && p.db) x = p.wcol ? __ldg(p.wcol + r) : 1.0f;
+                    for (int j = 0; j < 8; ++j) v[u][j] = (r0 + ku * 8 + j < R) ? __ldg(src + j * ld) : 0.0f;
+                    dst[u] = (isa ? sA : sB) + tc::unit_offset(col, ku, kc_units);
+                    split[u] = isa ? a_split : b_split;
+                } else {
+                    if (lane >= n_extra) continue;
+                    const int ku = it0 - items_a - items_b;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t r = r0 + ku * 8 + j;
+                        float x = 0.0f;
+                        if (r < R) {
+                            if (lane < p.n2) x = __ldg(p.Y2 + r * p.rs2 + lane * p.cs2);
+                            else if (lane == p.n2 && p.db) x = p.wcol ? __ldg(p.wcol + r) : 1.0f;
+                        }
+                        v[u][j] = x;
                     }
-                    v[j] = x;
+                    dst[u] = sB + tc::unit_offset(N + lane, ku, kc_units);
+                    split[u] = b_split;
                 }
-                dst = sB + tc::unit_offset(N + lane, ku, kc_units);
-                split = b_split;
             }
-            uint4 hi, lo;
-            tc::split_bf16x8(v, hi, lo, true);
-            *reinterpret_cast<uint4 *>(dst) = hi;
-            *reinterpret_cast<uint4 *>(dst + split) = lo;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!dst[u]) continue;
+                uint4 hi, lo;
+                tc::split_bf16x8(v[u], hi, lo, true);
+                *reinterpret_cast<uint4 *>(dst[u]) = hi;
+                *reinterpret_cast<uint4 *>(dst[u] + split[u]) = lo;
+            }
         }
         tc::fence_proxy_async();
         tc::fence_before_sync();
@@ -315,22 +337,32 @@ __global__ void __launch_bounds__(kNT) k_bwd_gemm_tn_tc(const TnParams p)
         tc::mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));
         tc::fence_after_sync();
     }
-    const int m = (warp & 3) * 32 + lane;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const int n_w = N + p.n2;  // columns [0, n_w) go to dW, column n_w to db
+    // D (lane = row m) -> shared memory [m][Nt + 1] (the stages are free now) -> atomics with lane = column n: a warp adds
+    // to 128 contiguous bytes of one row of dW instead of to 32 different rows
+    float *sD = reinterpret_cast<float *>(smem);
+    const int ldd = Nt + 1;
+    {
+        const int m = (warp & 3) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
 #pragma unroll 1
-    for (int cc = warp >> 2; cc < Nt / 16; cc += 2) {
-        float z[16];
-        tc::tmem_ld16(tmem_acc + lane_off + cc * 16, z);
-        if (m < Mv) {
-            float *dw = p.dW + (int64_t)(m0 + m) * p.ldw;
+        for (int cc = warp >> 2; cc < Nt / 16; cc += kNT / kRows) {
+            float z[16];
+            tc::tmem_ld16(tmem_acc + lane_off + cc * 16, z);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = cc * 16 + j;
-                if (z[j] == 0.0f) continue;
-                if (n < n_w) atomicAdd(dw + n, z[j]);
-                else if (n == n_w && p.db) atomicAdd(p.db + m0 + m, z[j]);
-            }
+            for (int j = 0; j < 16; ++j) sD[m * ldd + cc * 16 + j] = z[j];
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    const int n_w = N + p.n2;  // columns [0, n_w) go to dW, column n_w to db
+    const int n_out = n_w + (p.db ? 1 : 0);
+    for (int m = warp; m < Mv; m += kNT / 32) {
+        float *dw = p.dW + (int64_t)(m0 + m) * p.ldw;
+        for (int n = lane; n < n_out; n += 32) {
+            const float v = sD[m * ldd + n];
+            if (v == 0.0f) continue;
+            if (n < n_w) atomicAdd(dw + n, v);
+            else atomicAdd(p.db + m0 + m, v);
         }
     }
     tc::fence_before_sync();

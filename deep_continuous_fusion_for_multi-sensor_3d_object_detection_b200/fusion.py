@@ -90,7 +90,8 @@ class FrameContext:
 
     def precompute(self, layers, shapes=None):
         """Launch the point tables of `layers` (and, if `shapes` = [(H,W)] is given, their KNN tables) ahead of use.
-        Inference only (no autograd through the tables)."""
+        The tables carry no autograd graph: a layer that needs gradients treats its table as an intermediate of its own
+        autograd Function (which differentiates through feat / W1 / b1 itself)."""
         if self.feat is None:
             raise ValueError("FrameContext.precompute: call gather() first")
         main = torch.cuda.current_stream(self.points.device)
@@ -103,7 +104,7 @@ class FrameContext:
         if multi:
             # one launch for every scale: the point features are packed into the tensor-core operand once
             Ts = [torch.empty((self.B, self.N, l.c_bev), dtype=torch.float32, device=dev) for l in layers]
-            packed = [l._packed.w1(l.fc1.weight, l.mode) for l in layers]   # packs on the current (main) stream if stale
+            packed = [l._packed.w1(l.fc1.weight.detach(), l.mode) for l in layers]   # packs on the current (main) stream if stale
             st = streams[1]
             st.wait_stream(main)
             with torch.cuda.stream(st), torch.no_grad():
@@ -323,7 +324,9 @@ class ContinuousFusion(nn.Module):
         needs_grad = torch.is_grad_enabled() and (bev.requires_grad or frames.feat.requires_grad or
                                                   any(p.requires_grad for p in self.parameters()))
         if needs_grad:
-            out = _FusionFunction.apply(*args, None, None)
+            # a table launched ahead by FrameContext.precompute is only an intermediate of this Function: its gradient
+            # path (feat, W1, b1) is the Function's own backward, so it can be used here as well
+            out = _FusionFunction.apply(*args, frames.table_for(self), None)
         else:
             with torch.no_grad():
                 out = _FusionFunction.forward(_NullCtx(), *[a.detach() if isinstance(a, torch.Tensor) else a for a in args],

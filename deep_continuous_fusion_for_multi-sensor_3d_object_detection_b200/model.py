@@ -228,8 +228,9 @@ class ObjectDetection_DCF(nn.Module):
             else:
                 frames.gather(img_feat, calib=self.calib, img_size=size)
 
-            if not torch.is_grad_enabled():
-                frames.precompute([self.fusion[f"group{g}"] for g in self.fusion_scales])
+            # K-4a of every scale in one launch, on a side stream (training too: the tables are intermediates of each
+            # layer's autograd Function, not autograd leaves)
+            frames.precompute([self.fusion[f"group{g}"] for g in self.fusion_scales])
 
             inplace = not torch.is_grad_enabled()   # inference: the group's output map is fused in place (no copy of the
                                                     # ~2/3 of the cells that have no LiDAR point in reach)

@@ -27,6 +27,8 @@ size_t bwd_tc_packed_bytes(int32_t Nn, int32_t Kd);
 bool bwd_tc_nn_fits(int32_t Kd, int32_t N);
 bool bwd_tc_tn_fits(int32_t M, int32_t N);
 int bwd_tc_pack(const float *d_W, int32_t ld, int32_t Nn, int32_t Kd, int transpose, void *d_img, cudaStream_t st);
+int bwd_tc_pack4(const float *const *Ws, const int32_t *lds, const int32_t *Nns, const int32_t *Kds, const int *transposes,
+                 void *const *imgs, int n, cudaStream_t st);
 int bwd_tc_gemm_nn(const float *X, int64_t ldx, int64_t R, const int32_t *d_R, int32_t Kd, int32_t N, const void *wimg,
                    float *Out, int64_t ldo, int epi, const float *aux, int64_t ldaux, cudaStream_t st);
 int bwd_tc_gemm_tn(const float *X, int64_t ldx, int32_t M, const float *Y, int64_t ldy, int32_t N, const float *Y2,
@@ -524,10 +526,24 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     }
     k_bwd_h1<<<blocks_for(rows, 8), 256, 0, st>>>(T, w.row_pt, w.row_cx, w.row_cy, w.counters, C, d_W1, Ci, w.H1);
     launches += 2;
+    if (tc_row_nn || tc_pt_nn) {  // operand images of W2, W2^T, W3^T (row side) and W1[:, :Ci]^T (dF) in one launch
+        const float *Ws[4];
+        int32_t lds[4], Nns[4], Kds[4];
+        int trs[4], n = 0;
+        void *imgs[4];
+        auto job = [&](const float *Wm, int32_t ld, int32_t Nn, int32_t Kd, int tr, void *img) {
+            Ws[n] = Wm; lds[n] = ld; Nns[n] = Nn; Kds[n] = Kd; trs[n] = tr; imgs[n] = img;
+            ++n;
+        };
+        if (tc_row_nn) {
+            job(d_W2, C, C, C, 0, w.pW2);
+            job(d_W2, C, C, C, 1, w.pW2t);
+            job(d_W3, C, C, C, 1, w.pW3t);
+        }
+        if (tc_pt_nn) job(d_W1, ldw1, Ci, C, 1, w.pW1t);
+        CF_TRY(bwd_tc_pack4(Ws, lds, Nns, Kds, trs, imgs, n, st));
+    }
     if (tc_row_nn) {
-        CF_TRY(bwd_tc_pack(d_W2, C, C, C, 0, w.pW2, st));
-        CF_TRY(bwd_tc_pack(d_W2, C, C, C, 1, w.pW2t, st));
-        CF_TRY(bwd_tc_pack(d_W3, C, C, C, 1, w.pW3t, st));
         // H2 = relu(H1 W2^T + b2)
         CF_TRY(bwd_tc_gemm_nn(w.H1, C, rows, n_rows, C, C, w.pW2, w.H2, C, EPI_BIAS_RELU, d_b2, 0, st));
     } else {
@@ -568,6 +584,8 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     }
 
     // ---- layer 2 ------------------------------------------------------------------------------------------------------
+    // (masking each cell's dPooled row straight into the cell's rows of H2 in the GEMM epilogue was measured: the
+    //  thread = cell, row-strided read-modify-write costs 4x the separate pass below)
     k_bwd_dz2<<<blocks_for(rows * C, 256), 256, 0, st>>>(w.H2, w.dPooled, w.row_cell, w.counters, C);  // H2 now holds dZ2
     ++launches;
     if (tc_row_tn) {
@@ -622,7 +640,6 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     }
     // dF += dT W1[:, :Ci]
     if (tc_pt_nn) {
-        CF_TRY(bwd_tc_pack(d_W1, ldw1, Ci, C, 1, w.pW1t, st));
         CF_TRY(bwd_tc_gemm_nn(w.dT, C, pts, nullptr, C, Ci, w.pW1t, d_gfeat, Ci, EPI_ACCUM, nullptr, 0, st));
     } else {
         k_sgemm_nn<<<dim3((unsigned)ceil_div64(pts, 64), (unsigned)((Ci + 63) / 64)), 256, 0, st>>>(

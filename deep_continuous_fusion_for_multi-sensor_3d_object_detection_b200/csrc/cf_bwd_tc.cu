@@ -46,6 +46,35 @@ __global__ void __launch_bounds__(256) k_bwd_pack(const float *__restrict__ W, i
     *reinterpret_cast<uint4 *>(img + base + split_bytes) = lo;
 }
 
+// the same for up to four images in one launch (blockIdx.y = image)
+struct PackJob {
+    const float *W;
+    int32_t ld, Nn, Kd, KC, transpose;
+    uint8_t *img;
+};
+struct PackJobs {
+    PackJob j[4];
+};
+__global__ void __launch_bounds__(256) k_bwd_pack_multi(const PackJobs jobs)
+{
+    const PackJob &q = jobs.j[blockIdx.y];
+    const int32_t units = q.Nn * (q.Kd / 8);
+    for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+        const int32_t n = u / (q.Kd / 8), k8 = u - n * (q.Kd / 8);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            v[i] = q.transpose ? __ldg(q.W + (size_t)(k8 * 8 + i) * q.ld + n) : __ldg(q.W + (size_t)n * q.ld + k8 * 8 + i);
+        uint4 hi, lo;
+        tc::split_bf16x8(v, hi, lo, true);
+        const int32_t kc_units = q.KC / 8, chunk = k8 / kc_units, ku = k8 - chunk * kc_units;
+        const size_t split_bytes = (size_t)q.Nn * q.KC * 2;
+        const size_t base = (size_t)chunk * 2 * split_bytes + tc::unit_offset(n, ku, kc_units);
+        *reinterpret_cast<uint4 *>(q.img + base) = hi;
+        *reinterpret_cast<uint4 *>(q.img + base + split_bytes) = lo;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // NN: tile = 128 rows of X.  The whole packed weight image stays in shared memory; X is converted K-chunk by K-chunk.
 // ---------------------------------------------------------------------------------------------------------------
@@ -387,6 +416,20 @@ int bwd_tc_pack(const float *d_W, int32_t ld, int32_t Nn, int32_t Kd, int transp
 {
     const int32_t units = Nn * (Kd / 8);
     k_bwd_pack<<<(units + 255) / 256, 256, 0, st>>>(d_W, ld, Nn, Kd, nn_kc(Kd), transpose, (uint8_t *)d_img);
+    count_launches(1);
+    return launch_status("cf_fusion_bwd (pack)");
+}
+
+int bwd_tc_pack4(const float *const *Ws, const int32_t *lds, const int32_t *Nns, const int32_t *Kds, const int *transposes,
+                 void *const *imgs, int n, cudaStream_t st)
+{
+    PackJobs jobs{};
+    int32_t most = 0;
+    for (int i = 0; i < n; ++i) {
+        jobs.j[i] = PackJob{Ws[i], lds[i], Nns[i], Kds[i], nn_kc(Kds[i]), transposes[i], (uint8_t *)imgs[i]};
+        most = std::max(most, Nns[i] * (Kds[i] / 8));
+    }
+    k_bwd_pack_multi<<<dim3((unsigned)std::min((most + 255) / 256, 64), (unsigned)n), 256, 0, st>>>(jobs);
     count_launches(1);
     return launch_status("cf_fusion_bwd (pack)");
 }

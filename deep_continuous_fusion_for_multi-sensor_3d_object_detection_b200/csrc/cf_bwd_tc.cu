@@ -91,6 +91,7 @@ struct NnParams {
     int32_t epi;
     const float *aux;  // EPI_BIAS_RELU: bias[N];  EPI_MASK: mask (R x N, row stride ldaux), may alias Out
     int64_t ldaux;
+    int32_t stage_cols;  // columns of the accumulator staged through shared memory per epilogue pass (multiple of 32)
 };
 
 __global__ void __launch_bounds__(kNT) k_bwd_gemm_nn_tc(const NnParams p)
@@ -181,45 +182,47 @@ __global__ void __launch_bounds__(kNT) k_bwd_gemm_nn_tc(const NnParams p)
             phase ^= 1u;
             tc::fence_after_sync();
         }
-        const int64_t r = r0 + row;
-        const bool live = r < R;
+        // accumulator (lane = row) -> shared memory over the A buffer (the MMAs are done with it), 16-byte columns XOR-swizzled
+        // by the row so that both the row-wise writes and the column-wise reads are conflict free -> epilogue with
+        // consecutive lanes on consecutive 16-byte columns: a warp touches 512 contiguous bytes of Out instead of 32 rows
+        const int n4 = p.stage_cols / 4;  // 16-byte columns per pass (all of N when the tile fits beside the weights)
+        float4 *sD = reinterpret_cast<float4 *>(sA);
+        const int live_rows = (int)min((int64_t)kRows, R - r0);
         __syncwarp();
 #pragma unroll 1
-        for (int cc = grp; cc < N / 32; cc += kNT / kRows) {
-            float z[32];
-            tc::tmem_ld32(tmem_acc + lane_off + cc * 32, z);
-            if (live) {
-                float4 *dst = reinterpret_cast<float4 *>(p.Out + r * p.ldo + cc * 32);
+        for (int c0 = 0; c0 < N; c0 += p.stage_cols) {
+            if (c0) __syncthreads();  // the previous pass has been read
+#pragma unroll 1
+            for (int cc = grp; cc < p.stage_cols / 32; cc += kNT / kRows) {
+                float z[32];
+                tc::tmem_ld32(tmem_acc + lane_off + c0 + cc * 32, z);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    sD[row * n4 + ((cc * 8 + q) ^ (row & 7))] = make_float4(z[q * 4], z[q * 4 + 1], z[q * 4 + 2], z[q * 4 + 3]);
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+            for (int i = tid; i < live_rows * n4; i += kNT) {
+                const int m = i / n4, c4 = i - m * n4;
+                const float4 z = sD[m * n4 + (c4 ^ (m & 7))];
+                float4 *dst = reinterpret_cast<float4 *>(p.Out + (r0 + m) * p.ldo + c0) + c4;
                 if (p.epi == EPI_ACCUM) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 o = dst[q];
-                        dst[q] = make_float4(o.x + z[q * 4], o.y + z[q * 4 + 1], o.z + z[q * 4 + 2], o.w + z[q * 4 + 3]);
-                    }
+                    const float4 o = *dst;
+                    *dst = make_float4(o.x + z.x, o.y + z.y, o.z + z.z, o.w + z.w);
                 } else if (p.epi == EPI_BIAS_RELU) {
-                    const float4 *bias = reinterpret_cast<const float4 *>(p.aux + cc * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(bias + q);
-                        dst[q] = make_float4(fmaxf(z[q * 4] + b.x, 0.f), fmaxf(z[q * 4 + 1] + b.y, 0.f),
-                                             fmaxf(z[q * 4 + 2] + b.z, 0.f), fmaxf(z[q * 4 + 3] + b.w, 0.f));
-                    }
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.aux + c0) + c4);
+                    *dst = make_float4(fmaxf(z.x + bv.x, 0.f), fmaxf(z.y + bv.y, 0.f), fmaxf(z.z + bv.z, 0.f), fmaxf(z.w + bv.w, 0.f));
                 } else if (p.epi == EPI_MASK) {
-                    const float4 *mk = reinterpret_cast<const float4 *>(p.aux + r * p.ldaux + cc * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 m = mk[q];  // read before the (possibly aliasing) store of the same elements
-                        dst[q] = make_float4(m.x > 0.f ? z[q * 4] : 0.f, m.y > 0.f ? z[q * 4 + 1] : 0.f,
-                                             m.z > 0.f ? z[q * 4 + 2] : 0.f, m.w > 0.f ? z[q * 4 + 3] : 0.f);
-                    }
+                    // read before the (possibly aliasing) store of the same elements
+                    const float4 mk = *(reinterpret_cast<const float4 *>(p.aux + (r0 + m) * p.ldaux + c0) + c4);
+                    *dst = make_float4(mk.x > 0.f ? z.x : 0.f, mk.y > 0.f ? z.y : 0.f, mk.z > 0.f ? z.z : 0.f, mk.w > 0.f ? z.w : 0.f);
                 } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) dst[q] = make_float4(z[q * 4], z[q * 4 + 1], z[q * 4 + 2], z[q * 4 + 3]);
+                    *dst = z;
                 }
             }
         }
         tc::fence_before_sync();
-        __syncthreads();  // every warp has drained the accumulator before the next tile's first MMA overwrites it
+        __syncthreads();  // accumulator and staging buffer are drained before the next tile overwrites them
         tc::fence_after_sync();
     }
     __syncthreads();
@@ -438,8 +441,14 @@ int bwd_tc_gemm_nn(const float *X, int64_t ldx, int64_t R, const int32_t *d_R, i
                    float *Out, int64_t ldo, int epi, const float *aux, int64_t ldaux, cudaStream_t st)
 {
     static int attr_done = 0;
-    NnParams p{X, ldx, R, d_R, Kd, N, nn_kc(Kd), (const uint8_t *)wimg, Out, ldo, epi, aux, ldaux};
-    const int smem = 2 * N * Kd * 2 + 2 * kRows * p.KC * 2;
+    NnParams p{X, ldx, R, d_R, Kd, N, nn_kc(Kd), (const uint8_t *)wimg, Out, ldo, epi, aux, ldaux, 0};
+    // weights + max(A chunk, staged accumulator columns): the 32-column groups of the 128-row tile that fit into the A
+    // buffer, or into 32 KB where the A chunk is smaller (more would cost residency), as a divisor of N / 32 (full passes)
+    const int w_bytes = 2 * N * Kd * 2, a_bytes = 2 * kRows * p.KC * 2, group_bytes = kRows * 32 * 4;
+    int groups = std::max(1, std::min(N / 32, std::max(a_bytes, std::min(220 * 1024 - w_bytes, 32 * 1024)) / group_bytes));
+    while ((N / 32) % groups) --groups;
+    p.stage_cols = groups * 32;
+    const int smem = w_bytes + std::max(a_bytes, groups * group_bytes);
     if (!attr_done) {
         CF_TRY(cuda_status(cudaFuncSetAttribute(k_bwd_gemm_nn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024),
                            "cf_fusion_bwd (nn attr)"));

@@ -27,6 +27,48 @@ def test_library_exports_every_declared_symbol(dcf):
     assert sorted(dcf._lib.SIGNATURES) == names
 
 
+def _declared_prototypes():
+    """name -> list of C parameter declarations, parsed from the header."""
+    text = open(os.path.join(ROOT, "include", "cf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"CF_API\s+[\w\s\*]+?\b(cf_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = " ".join(m.group(2).split())
+        protos[m.group(1)] = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+    return protos
+
+
+def _kind(c_decl):
+    """Coarse class of a C parameter: pointer / i32 / i64 / f32 / size."""
+    if "*" in c_decl:
+        return "ptr"
+    for key, kind in (("int64_t", "i64"), ("int32_t", "i32"), ("size_t", "size"), ("float", "f32"), ("double", "f64"),
+                      ("int", "i32")):
+        if re.search(rf"\b{key}\b", c_decl):
+            return kind
+    raise AssertionError(f"unclassified parameter: {c_decl}")
+
+
+def test_ctypes_signatures_match_the_header(dcf):
+    """Every entry of the ctypes table has the argument COUNT and the argument KINDS (pointer / int32 / int64 / float /
+    size_t, in order) of its prototype in include/cf_b200.h -- a stale table would shift every later argument."""
+    protos = _declared_prototypes()
+    table = dcf._lib.SIGNATURES
+    assert sorted(protos) == sorted(table)
+
+    def ctype_kind(t):
+        if t is ctypes.c_void_p or t is ctypes.c_char_p or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int32: "i32", ctypes.c_int: "i32", ctypes.c_int64: "i64", ctypes.c_longlong: "i64",
+                ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_size_t: "size"}[t]
+
+    for name, params in protos.items():
+        _, argtypes = table[name]
+        assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters, ctypes table {len(argtypes)}"
+        for i, (decl, t) in enumerate(zip(params, argtypes)):
+            assert _kind(decl) == ctype_kind(t), f"{name}: parameter {i} `{decl}` bound as {t}"
+
+
 def test_abi_version_and_error_channel(dcf):
     lib = dcf.load()
     assert lib.cf_abi_version() == 2

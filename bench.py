@@ -467,10 +467,7 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if mode in ("fp32", "simt") else "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: BASELINE.json {CONFIG_OF.get(args.workload, 'custom')} (batch {B}/GPU, K={K}, "
-                               f"{len(wl['scales'])} scales of a {wl['workload']['bev'][0]}x{wl['workload']['bev'][1]} BEV, "
-                               f"~{int(n_valid)} LiDAR points/frame, 128x120x160 camera map)",
-                   "mlp_mode": mode, "frames_per_step_per_gpu": B, "launch": "eager" if graph is None else "cuda_graph_replay", "l2_policy": "inputs_exceed_l2 (BEV in+out "
+        "config": {"workload": workload_label(args.workload, wl), "mlp_mode": mode, "frames_per_step_per_gpu": B, "launch": "eager" if graph is None else "cuda_graph_replay", "l2_policy": "inputs_exceed_l2 (BEV in+out "
                    f"{2 * sum(b.numel() * 4 for b in pipe.bev) / 1e6:.0f} MB per step vs 126 MB L2)"},
         "e2e": {"value": round(dcf.dist_util.aggregate_rate(B, world, e2e_steps, ms_e2e), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
@@ -486,6 +483,14 @@ def run_gpu(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def workload_label(name, wl):
+    """One string for both arms: the workload's key, the BASELINE.json entry it stands for, and its sizes."""
+    ci, hf, wf = wl["img_feat"].shape[1:]
+    return (f"{name}: BASELINE.json {CONFIG_OF.get(name, 'custom')} (batch {wl['points'].shape[0]}/GPU, K={wl['k']}, "
+            f"{len(wl['scales'])} scales of a {wl['workload']['bev'][0]}x{wl['workload']['bev'][1]} BEV, "
+            f"~{int(float(np.mean(wl['num_points'])))} LiDAR points/frame, {ci}x{hf}x{wf} camera map)")
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -510,8 +515,7 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": max(args.warmup, 0),
             "ms_per_step": round(1e3 * B / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: BASELINE.json {CONFIG_OF.get(args.workload, 'custom')}",
-                       "frames_per_step_per_gpu": B},
+            "config": {"workload": workload_label(args.workload, wl), "frames_per_step_per_gpu": B},
             "cpu_baseline": {"value": round(v, 6), "unit": UNIT, "cores": nthr, "kind": "port", "sample": desc},
             "e2e": {"value": round(v, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -48,9 +48,36 @@ def edge_case_boxes():
     return np.array(b, dtype=np.float32)
 
 
+def chain_fixture():
+    """The evaluator's chain on a decoded prediction map (test.py:79-85): split -> get_bboxes -> NMS_SAT.  The box
+    channels hold decoded car-sized boxes (model.py:129 guarantees l, w > 0), ~3 % of the anchors pass the score."""
+    rng = np.random.default_rng(19)
+    B, H, W = 3, 44, 50
+    cls = rng.random((B, 4, H, W)).astype(np.float32) * 0.7
+    for a in (1, 3):
+        cls[:, a] = np.where(rng.random((B, H, W)) < 0.035, 0.8 + 0.2 * rng.random((B, H, W)), cls[:, a]).astype(np.float32)
+    cls[2, 1] = 0.1
+    cls[2, 3] = 0.2                                  # a frame without detections
+    box = np.zeros((B, 14, H, W), np.float32)
+    for a in range(2):
+        bx = car_boxes(rng, B * H * W, x=(0, 70), y=(-30, 30)).reshape(B, H, W, 7)
+        box[:, 7 * a:7 * a + 7] = bx.transpose(0, 3, 1, 2)
+    boxes = R.get_bboxes(torch.from_numpy(cls), torch.from_numpy(box), 0.8)
+    keep = R.nms_sat(boxes)
+    data = dict(cls=cls, box=box, thr=np.float32(0.8), counts=np.array([b.shape[0] for b in boxes]))
+    for b in range(B):
+        data[f"boxes_{b}"] = boxes[b].numpy().reshape(-1, 7)
+        data[f"keep_{b}"] = keep[b]
+        print("chain frame", b, boxes[b].shape[0], "->", len(keep[b]))
+    np.savez_compressed(os.path.join(OUT, "postprocess_chain.npz"), **data)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = R.load()
+    if "--only-chain" in sys.argv:
+        return chain_fixture()
+    chain_fixture()
     # ---- NMS_SAT keep lists (test.py:142-175)
     frames = {}
     for n in (0, 1, 2, 50, 200, 600, 2000):

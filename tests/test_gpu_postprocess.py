@@ -119,3 +119,27 @@ def test_get_bboxes_golden_and_order(dcf, golden, oracle):
         assert int(raw[b]) == ref.shape[0] and np.array_equal(boxes[b, :ref.shape[0]].cpu().numpy(), ref)
     with pytest.raises(RuntimeError, match="exceed cap"):
         dcf.PostProcess(cap=64).get_bboxes(torch.from_numpy(cls), torch.from_numpy(box), 0.8)
+
+
+def test_on_device_chain_get_bboxes_then_nms_golden(dcf, golden):
+    """the evaluator's chain test.py:79-85 (split -> get_bboxes -> NMS_SAT) without leaving the device:
+    cf_get_bboxes writes the padded (B,cap,7) buffer + counts that cf_nms_sat consumes.  Boxes and keep-lists are
+    bit-exact against what the reference's own Test.get_bboxes / Test.NMS_SAT produce on the same prediction map
+    (oracle/gen_golden.py: chain_fixture), including a frame without detections."""
+    g = golden("postprocess_chain.npz")
+    pp = dcf.PostProcess(cap=1024)
+    pred = torch.cat([torch.from_numpy(g["cls"]), torch.zeros(3, 14, 44, 50), torch.from_numpy(g["box"])], 1).cuda()
+    pred_cls, _, pred_box = torch.split(pred, [4, 14, 14], dim=1)            # test.py:79
+    boxes, counts, raw = pp.get_bboxes_padded(pred_cls, pred_box, float(g["thr"]))
+    keep, kcnt = dcf.ops.nms_sat(boxes, counts)                              # device buffers straight through
+    torch.cuda.synchronize()
+    assert counts.tolist() == g["counts"].tolist() == raw.tolist()
+    for b in range(3):
+        n = int(g["counts"][b])
+        assert np.array_equal(boxes[b, :n].cpu().numpy(), g[f"boxes_{b}"])
+        assert np.array_equal(keep[b, :int(kcnt[b])].cpu().numpy(), g[f"keep_{b}"]), f"frame {b}"
+        assert (keep[b, int(kcnt[b]):] == -1).all()
+    # and the reference-shaped methods give the same rows
+    rows = pp.NMS_SAT(pp.get_bboxes(pred_cls, pred_box, float(g["thr"])))
+    assert [len(r) for r in rows] == [len(g[f"keep_{b}"]) for b in range(3)]
+    assert torch.equal(torch.stack(rows[0]).cpu(), torch.from_numpy(g["boxes_0"][g["keep_0"]]))

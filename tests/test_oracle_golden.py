@@ -111,3 +111,13 @@ def test_voxelize_project_restatement_matches_reference(oracle, golden, dcf, tag
     assert np.abs(uv[:n + 8] - g["projected_loc_uv"]).max() < 2e-3            # BLAS vs explicit summation order
     # host helpers reproduce pc_to_voxel_indice and the float32 thresholds
     assert dcf.geometry.voxel_matrix(cfg) == oracle.voxel_matrix(cfg) == (5, 4, 10, 0, 120, 24)
+
+
+def test_postprocess_chain(oracle, golden):
+    """The evaluator's chain (test.py:79-85: get_bboxes -> NMS_SAT) as run by the reference on one prediction map."""
+    g = golden("postprocess_chain.npz")
+    for b in range(3):
+        boxes = oracle.get_bboxes(g["cls"][b], g["box"][b], float(g["thr"]))
+        assert boxes.shape[0] == int(g["counts"][b]) and np.array_equal(boxes.reshape(-1, 7), g[f"boxes_{b}"])
+        keep = oracle.nms_sat(boxes) if boxes.shape[0] else np.zeros((0,), np.int32)
+        assert np.array_equal(keep, g[f"keep_{b}"])

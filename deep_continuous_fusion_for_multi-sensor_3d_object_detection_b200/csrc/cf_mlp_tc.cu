@@ -38,6 +38,28 @@
 
 namespace cf {
 
+// tuning aids (A/B measurements only), read from the environment ONCE, when the library first launches a fused kernel
+struct Tuning {
+    int max_ctas = 0;             // CF_MAX_CTAS: cap on resident CTAs per SM of the persistent fused kernels
+    bool debug_launch = false;    // CF_DEBUG_LAUNCH: print the launch shape
+    bool no_skew = false;         // CF_NO_SKEW: never use the double-buffered kernel
+    bool no_strip = false;        // CF_NO_STRIP: never use the strip pipeline (cf_fusion_strip.cu)
+    long long compact_min_tiles = -1;   // CF_COMPACT_MIN_TILES
+};
+static const Tuning &tuning()
+{
+    static const Tuning t = [] {
+        Tuning v;
+        if (const char *e = getenv("CF_MAX_CTAS")) v.max_ctas = atoi(e);
+        v.debug_launch = getenv("CF_DEBUG_LAUNCH") != nullptr;
+        v.no_skew = getenv("CF_NO_SKEW") != nullptr;
+        v.no_strip = getenv("CF_NO_STRIP") != nullptr;
+        if (const char *e = getenv("CF_COMPACT_MIN_TILES")) v.compact_min_tiles = atoll(e);
+        return v;
+    }();
+    return t;
+}
+
 namespace {
 
 constexpr int kTile = 128;  // cells per tile == UMMA M
@@ -1583,9 +1605,9 @@ int launch_tc(const TcParams &p, cudaStream_t st)
     int per_sm = 1;
     CF_TRY(resident_ctas(k_fusion_tc<C, NS>, NT, smem, L::kTmemCols, &regs, &per_sm));
     per_sm = std::max(1, per_sm);
-    if (const char *cap = getenv("CF_MAX_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // tuning aid
+    if (tuning().max_ctas > 0) per_sm = std::max(1, std::min(per_sm, tuning().max_ctas));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
-    if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_tc<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
+    if (tuning().debug_launch) fprintf(stderr, "k_fusion_tc<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
     k_fusion_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
@@ -1599,7 +1621,7 @@ int launch_sk(const TcParams &p, cudaStream_t st)
     using L0 = TcLayout<C, NS>;
     constexpr int NT = kTile * TcShape<C>::G;
     const int smem = L::smem_bytes(p.K);
-    if (smem > 227 * 1024 || getenv("CF_NO_SKEW")) return CF_ERR_UNSUPPORTED;
+    if (smem > 227 * 1024 || tuning().no_skew) return CF_ERR_UNSUPPORTED;
     static int attr_bytes = 0, regs = 0, regs0 = 0;
     int per_sm = 0, per_sm0 = 0;
     CF_TRY(resident_ctas(k_fusion_sk<C, NS>, NT, smem, L::kTmemCols, &regs, &per_sm));
@@ -1610,14 +1632,19 @@ int launch_sk(const TcParams &p, cudaStream_t st)
                            "k_fusion_sk smem attribute"));
         attr_bytes = smem;
     }
-    if (const char *cap = getenv("CF_MAX_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));
+    if (tuning().max_ctas > 0) per_sm = std::max(1, std::min(per_sm, tuning().max_ctas));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
-    if (getenv("CF_DEBUG_LAUNCH")) fprintf(stderr, "k_fusion_sk<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
+    if (tuning().debug_launch) fprintf(stderr, "k_fusion_sk<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
     k_fusion_sk<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
 
 }  // namespace
+
+int fusion_strip(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H,
+                 int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1, int32_t Ci,
+                 const float *d_b2, const float *d_b3, float *d_out, int32_t mode, const uint8_t *img2, const uint8_t *img3,
+                 cudaStream_t st);
 
 static size_t tc_weight_bytes(int32_t C, int NS) { return ((size_t)2 * NS * C * C * 2 + 255) / 256 * 256; }
 
@@ -1661,19 +1688,25 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     // one contiguous blob, so the tiles are already either full or empty (empty tiles just copy bev -> out) and
     // compaction only adds a launch (measured: 123 -> 148 us at 88x100x192).  CF_COMPACT_MIN_TILES overrides (tuning aid).
     int64_t min_tiles = 4 * (int64_t)sm_count();
-    if (const char *e = getenv("CF_COMPACT_MIN_TILES")) min_tiles = atoll(e);
+    if (tuning().compact_min_tiles >= 0) min_tiles = tuning().compact_min_tiles;
+    if (!d_packed) {
+        const int pack_blocks = (C * (C / 8) + 255) / 256;
+        k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, (uint8_t *)d_workspace);
+        k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, (uint8_t *)d_workspace + (size_t)NS * C * C * 2);
+        count_launches(2);
+    }
+    // fine scales: the strip pipeline (bulk-copy engine for every BEV byte, no compaction pass)
+    if (!tuning().no_strip) {
+        const int rc = fusion_strip(d_bev, d_T, d_knn, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_b2, d_b3, d_out, mode, img2,
+                                    img3, st);
+        if (rc != CF_ERR_UNSUPPORTED) return rc;
+    }
     const bool compact = ceil_div64(n_cells, kTile) * B >= min_tiles;
     if (compact) {
         CF_TRY(cuda_status(cudaMemsetAsync(cell_count, 0, 512, st), "cf_fusion_fwd memset"));
         k_cell_compact<<<dim3((unsigned)ceil_div64(n_cells, 256), (unsigned)B), 256, 0, st>>>(d_knn, K, n_cells, cell_list,
                                                                                             cell_count);
         count_launches(1);
-    }
-    if (!d_packed) {
-        const int pack_blocks = (C * (C / 8) + 255) / 256;
-        k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W2, C, C, C, KC, NS, (uint8_t *)d_workspace);
-        k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, (uint8_t *)d_workspace + (size_t)NS * C * C * 2);
-        count_launches(2);
     }
     TcParams p;
     p.bev = d_bev; p.T = d_T; p.knn = d_knn; p.out = d_out; p.wimg2 = img2; p.wimg3 = img3; p.W1 = d_W1;

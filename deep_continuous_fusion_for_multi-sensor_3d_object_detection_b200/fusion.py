@@ -15,6 +15,9 @@ from . import geometry as G
 from . import ops
 
 
+TENSOR_CORE_WIDTHS = (32, 64, 96, 128, 192, 256)   # C with a tcgen05 instantiation of cf_fusion_fwd (cf_mlp_tc.cu)
+MAX_FRAMES_PER_CALL = 64                            # cf_fusion_fwd: frames per call on the tensor-core path
+
 _STREAM_POOL = {}   # device index -> side streams, shared by every FrameContext (creating streams per frame is not free)
 
 
@@ -26,6 +29,9 @@ class FrameContext:
             raise ValueError(f"pointcloud_raw: expected (B,N,3), got {tuple(points.shape)}")
         self.points = ops._contig(points, "pointcloud_raw", torch.float32, 3)
         self.B, self.N = self.points.shape[:2]
+        if self.B > MAX_FRAMES_PER_CALL:
+            raise ValueError(f"FrameContext: {self.B} frames per call; the fused kernels take at most {MAX_FRAMES_PER_CALL} "
+                             f"(split the batch)")
         self.num_points = ops.as_counts(num_points, self.B, self.points.device)
         self.grid = grid
         self.feat = None
@@ -36,6 +42,8 @@ class FrameContext:
         main = torch.cuda.current_stream(self.points.device)
         st = self._side_streams(1)[0]
         st.wait_stream(main)
+        self.points.record_stream(st)       # read by the bucketing stream
+        self.num_points.record_stream(st)
         with torch.cuda.stream(st):
             self.bucket_start, self.sorted_pts, self._bucket_ws = ops.bucket_points(self.points, self.num_points, grid)
             self._bucket_done = torch.cuda.Event()
@@ -113,6 +121,7 @@ class FrameContext:
                 ev = torch.cuda.Event()
                 ev.record(st)
             for l, T in zip(layers, Ts):
+                T.record_stream(st)   # allocated on main's pool, written on st: the block must not be reused before st is done
                 self._tables[id(l)] = (T, ev)
         for layer, st in zip([] if multi else layers, streams[1:]):
             T = torch.empty((self.B, self.N, layer.c_bev), dtype=torch.float32, device=dev)
@@ -123,6 +132,7 @@ class FrameContext:
                                out=T, packed=packed)
                 ev = torch.cuda.Event()
                 ev.record(st)
+            T.record_stream(st)
             self._tables[id(layer)] = (T, ev)
         if shapes is not None:
             # The search runs on the bucketing stream (it only needs K-1, not the gather).  Only the largest map is
@@ -216,6 +226,14 @@ class FusionRunner:
             frames.gather(self.img_feat, calib=self.calib, img_size=self.img_size)
             return fuse_scales(frames, self.layers, self.bevs, inplace=self.inplace)
 
+    def refresh_weights(self):
+        """Re-pack the tensor-core operand images of every layer from its current weights (in place: the captured graph
+        reads the same buffers).  Call after an optimizer step / load_state_dict and before the next replay -- a replay never
+        re-packs by itself unless the pack kernels were part of the capture."""
+        with torch.no_grad():
+            for l in self.layers:
+                l._packed.refresh(l.fc1.weight, l.fc2.weight, l.fc3.weight, l.mode)
+
     def __call__(self):
         self.graph.replay()
         return self.outs
@@ -288,8 +306,14 @@ class ContinuousFusion(nn.Module):
         super().__init__()
         if not (1 <= k <= 16):
             raise ValueError("k must be in [1, 16]")
+        if mode not in ("fp32", "bf16", "simt"):
+            raise ValueError(f"mode must be 'fp32', 'bf16' or 'simt', got {mode!r}")
         if c_bev % 16 or not (16 <= c_bev <= 256):
             raise ValueError("c_bev must be a multiple of 16 in [16, 256]")
+        if mode != "simt" and c_bev not in TENSOR_CORE_WIDTHS:
+            # the tcgen05 kernels are instantiated for the backbone's widths; anything else would only fail at the first forward
+            raise ValueError(f"c_bev={c_bev} has no tensor-core instantiation (modes 'fp32' / 'bf16' support {TENSOR_CORE_WIDTHS}); "
+                             f"use mode='simt' for other multiples of 16")
         if c_img % 4:
             raise ValueError("c_img must be a multiple of 4")
         self.c_img, self.c_bev, self.k, self.radius, self.mode = c_img, c_bev, int(k), float(radius), mode

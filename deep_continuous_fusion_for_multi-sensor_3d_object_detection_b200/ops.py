@@ -41,6 +41,36 @@ def as_counts(num_points, B: int, device) -> torch.Tensor:
     return num_points.contiguous()
 
 
+_CALIB_CACHE = {}
+
+
+def _calib_host(calib):
+    """(4,3) CRT_tensor -> ctypes float[12].  A device tensor (the drop-in model registers it as a buffer that .cuda()
+    moves) is copied to the host ONCE per (storage, version): the calls stay free of host synchronisation afterwards and
+    remain capturable in a CUDA graph."""
+    if isinstance(calib, torch.Tensor):
+        key = (calib.data_ptr(), calib._version, calib.device)
+        hit = _CALIB_CACHE.get(key)
+        if hit is not None:
+            return hit
+        if calib.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("calib: first use of a device-resident CRT_tensor inside CUDA-graph capture; call the layer "
+                               "once before capturing (or pass a host array)")
+        arr = calib.detach().to("cpu", torch.float32).numpy()
+    else:
+        key = None
+        arr = np.asarray(calib, dtype=np.float32)
+    arr = np.ascontiguousarray(arr, dtype=np.float32)
+    if arr.shape != (4, 3):
+        raise ValueError(f"calib: expected (4,3) CRT_tensor, got {arr.shape}")
+    out = (C.c_float * 12)(*arr.reshape(-1).tolist())
+    if key is not None:
+        if len(_CALIB_CACHE) > 64:
+            _CALIB_CACHE.clear()
+        _CALIB_CACHE[key] = out
+    return out
+
+
 class BucketGrid:
     """Uniform BEV bucket grid (K-1) + the per-batch sorted point storage."""
 
@@ -86,9 +116,7 @@ def voxelize_project(raw, num_raw, config, calib, max_num_pc=None, workspace=Non
     Z, X, Y = int(config["voxel_channel"]), int(config["voxel_length"]), int(config["voxel_width"])
     N = int(config["max_num_pc"] if max_num_pc is None else max_num_pc)
     f6 = lambda v: (C.c_float * 6)(*[float(x) for x in v])
-    crt = np.ascontiguousarray(np.asarray(calib.detach().cpu() if isinstance(calib, torch.Tensor) else calib, dtype=np.float32))
-    if crt.shape != (4, 3):
-        raise ValueError(f"calib: expected CRT_tensor (4,3), got {crt.shape}")
+    crt = _calib_host(calib)
     need = lib.cf_voxelize_workspace_bytes(B, Nraw, Z, X, Y)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=raw.device)
@@ -97,7 +125,7 @@ def voxelize_project(raw, num_raw, config, calib, max_num_pc=None, workspace=Non
     uv = torch.empty((B, N, 2), dtype=torch.float32, device=raw.device)
     num = torch.empty((B,), dtype=torch.int64, device=raw.device)
     check(lib.cf_voxelize_project(ptr(raw), ptr(num_raw), B, Nraw, f6(G.lidar_range(config)), f6(G.voxel_matrix(config)), Z, X, Y,
-                                  (C.c_float * 12)(*crt.ravel().tolist()), float(config["image_height"]),
+                                  crt, float(config["image_height"]),
                                   float(config["image_width"]), N, ptr(vox), ptr(pts), ptr(uv), ptr(num), ptr(workspace),
                                   stream_ptr()), "cf_voxelize_project")
     return vox, pts, uv, num
@@ -140,11 +168,7 @@ def point_gather(img_feat, points, num_points, calib=None, uv=None, img_size=(64
         raise ValueError("pass exactly one of calib / uv")
     calib_arr = None
     if calib is not None:
-        calib_np = np.ascontiguousarray(calib.detach().cpu().numpy() if isinstance(calib, torch.Tensor) else calib,
-                                        dtype=np.float32)
-        if calib_np.shape != (4, 3):
-            raise ValueError(f"calib: expected (4,3) CRT_tensor, got {calib_np.shape}")
-        calib_arr = (C.c_float * 12)(*calib_np.reshape(-1).tolist())
+        calib_arr = _calib_host(calib)
     else:
         uv = _contig(uv, "uv", torch.float32, 3)
         if uv.shape != (B, N, 2):
@@ -167,6 +191,23 @@ class PackedWeights:
     def __init__(self):
         self._key1, self._buf1, self._key23, self._buf23 = None, None, None, None
 
+    def invalidate(self):
+        """Forget the cached keys: the next w1() / w23() re-packs (in place, so buffers captured by a CUDA graph see it)."""
+        self._key1 = self._key23 = None
+
+    def refresh(self, W1, W2, W3, mode):
+        """Re-pack every operand image now, on the current stream.  Call after the weights changed and before replaying a
+        CUDA graph that captured the layer (FusionRunner.refresh_weights does): replays read the images, they do not re-pack."""
+        self.invalidate()
+        return self.w1(W1, mode), self.w23(W2, W3, mode)
+
+    @staticmethod
+    def _repack_in_capture(W):
+        """While a TRAINING step is being captured (autograd on) the pack kernels are always emitted, so that every replay
+        re-packs from the weights the optimizer just updated, whatever ran between the last step and the capture.  An
+        inference capture (torch.no_grad, FusionRunner) keeps the images static: call refresh() when the weights change."""
+        return W.is_cuda and torch.is_grad_enabled() and torch.cuda.is_current_stream_capturing()
+
     @staticmethod
     def _key(*tensors, mode):
         return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors) + (mode,)
@@ -180,7 +221,7 @@ class PackedWeights:
         if Ci % 16 or Ci > 256 or C_out % 32:
             return None
         key = self._key(W1, mode=m)
-        if key != self._key1:
+        if key != self._key1 or self._repack_in_capture(W1):
             need = lib.cf_point_mlp1_workspace_bytes(Ci, C_out, m)
             if self._buf1 is None or self._buf1.numel() != need or self._buf1.device != W1.device:
                 self._buf1 = torch.empty((need,), dtype=torch.uint8, device=W1.device)   # else: repack in place, so a
@@ -197,7 +238,7 @@ class PackedWeights:
         if m == _lib.MODE_SIMT or Cc % 32:
             return None
         key = self._key(W2, W3, mode=m)
-        if key != self._key23:
+        if key != self._key23 or self._repack_in_capture(W2):
             need = lib.cf_fusion_packed_bytes(Cc, m)
             if self._buf23 is None or self._buf23.numel() != need or self._buf23.device != W2.device:
                 self._buf23 = torch.empty((need,), dtype=torch.uint8, device=W2.device)
@@ -259,6 +300,14 @@ def point_mlp1_multi(feat, points, num_points, W1s, b1s, packeds, mode="fp32", o
 def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None, workspace=None, packed=None):
     """K-4.  out = bev + W3 sum_k relu(W2 relu(T[idx_k] - e_cell) + b2) + n_valid b3."""
     lib = load()
+    _req(bev, "bev", torch.float32, 4)
+    if out is not None:
+        _req(out, "out", torch.float32, 4)
+        if out.shape != bev.shape or out.device != bev.device or not out.is_contiguous():
+            raise ValueError(f"fusion_fwd: out must be a contiguous (dense NCHW) tensor of bev's shape {tuple(bev.shape)} on "
+                             f"{bev.device}, got shape {tuple(out.shape)}, strides {out.stride()}, device {out.device}")
+        if out.data_ptr() == bev.data_ptr() and not bev.is_contiguous():
+            raise ValueError("fusion_fwd: in-place operation (out is bev) needs a contiguous (dense NCHW) map")
     bev = _contig(bev, "bev", torch.float32, 4)
     T = _contig(T, "T", torch.float32, 3)
     knn_idx = _contig(knn_idx, "knn_idx", torch.int32, 4)
@@ -327,9 +376,7 @@ def point_gather_bwd(grad_feat, img_like, points, num_points, calib=None, uv=Non
     sb, sc, sh, sw = gimg.stride()
     calib_arr = None
     if calib is not None:
-        calib_np = np.ascontiguousarray(calib.detach().cpu().numpy() if isinstance(calib, torch.Tensor) else calib,
-                                        dtype=np.float32)
-        calib_arr = (C.c_float * 12)(*calib_np.reshape(-1).tolist())
+        calib_arr = _calib_host(calib)
     else:
         uv = _contig(uv, "uv", torch.float32, 3)
     check(lib.cf_point_gather_bwd(ptr(grad_feat), ptr(gimg), sb, sc, sh, sw, B, Ci, Hf, Wf, ptr(points), ptr(uv), calib_arr,

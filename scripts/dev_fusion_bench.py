@@ -18,12 +18,15 @@ def main():
     ap.add_argument("--mode", default=None)
     ap.add_argument("--reps", type=int, default=15)
     ap.add_argument("--groups", default="")
+    ap.add_argument("--empty", action="store_true", help="no LiDAR points: every cell is a pure bev -> out copy")
     a = ap.parse_args()
     wl = dcf.synthetic.make_workload(a.workload, seed=100)
     mode = a.mode or wl["workload"]["mode"]
     dev = torch.device("cuda")
     ops = dcf.ops
     to = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    if a.empty:
+        wl["num_points"][:] = 0
     points, counts, img = to(wl["points"]), to(wl["num_points"]), to(wl["img_feat"])
     grid = ops.BucketGrid(*dcf.geometry.bucket_grid(wl["config"], None))
     size = (float(wl["config"]["image_width"]), float(wl["config"]["image_height"]))

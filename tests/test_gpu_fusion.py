@@ -133,6 +133,20 @@ def test_module_rejects_bad_inputs(dcf):
               torch.zeros(1, 8, 3, device="cuda"), torch.tensor([3]))
     with pytest.raises(ValueError):
         dcf.ContinuousFusion(32, 40)
+    for c in (48, 160, 224):       # multiples of 16 without a tensor-core instantiation: rejected at construction ...
+        with pytest.raises(ValueError, match="tensor-core"):
+            dcf.ContinuousFusion(32, c, mode="fp32")
+        dcf.ContinuousFusion(32, c, mode="simt")   # ... but fine on the CUDA-core path
+    bev = torch.zeros(1, 32, 4, 4, device="cuda")
+    T = torch.zeros(1, 8, 32, device="cuda")
+    knn = torch.full((1, 4, 4, 3), -1, dtype=torch.int32, device="cuda")
+    w = [torch.zeros(32, 35, device="cuda"), torch.zeros(32, 32, device="cuda"), torch.zeros(32, device="cuda"),
+         torch.zeros(32, 32, device="cuda"), torch.zeros(32, device="cuda")]
+    with pytest.raises(ValueError, match="out must be"):   # a strided / wrongly shaped output is never written through
+        dcf.ops.fusion_fwd(bev, T, knn, (0.0, 0.0, 1.0, 1.0), *w, out=torch.zeros(1, 32, 4, 8, device="cuda")[..., ::2])
+    cl = torch.zeros(1, 32, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)
+    with pytest.raises(ValueError, match="out must be|in-place"):
+        dcf.ops.fusion_fwd(cl, T, knn, (0.0, 0.0, 1.0, 1.0), *w, out=cl)
     with pytest.raises(ValueError):
         dcf.ContinuousFusion(32, 32, k=17)
 
@@ -191,9 +205,7 @@ def test_fusion_runner_graph_replay_matches_eager(dcf):
                                    layer.fc3.bias), sc["weights"]):
                     prm.copy_(dev(w))
         # weights changed in place: the packed operand images must be refreshed before the graph is replayed
-        for layer in layers:
-            layer._packed.w1(layer.fc1.weight, "fp32")
-            layer._packed.w23(layer.fc2.weight, layer.fc3.weight, "fp32")
+        runner.refresh_weights()
         runner.points.copy_(dev(wl["points"]))
         runner.num_points.copy_(dev(wl["num_points"]))
         runner.img_feat.copy_(dev(wl["img_feat"]))

@@ -23,6 +23,7 @@
 // bit-identical to it.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "cf_common.cuh"
 #include "cf_tcgen05.cuh"
@@ -62,6 +63,7 @@ struct StripParams {
     int32_t inplace;
     int32_t nb;          // strip buffers in use (2 .. kMaxNB)
     int32_t strip_bytes; // bytes of one strip buffer: C * S * 4 + round16(S * K * 4)
+    int32_t debug;       // CF_STRIP_DEBUG bits (timing experiments only; results are wrong when set)
 };
 
 // the "row" a (cell, k) slot without a neighbour gathers: relu(-1e30 - e) = 0
@@ -563,9 +565,10 @@ __global__ void __launch_bounds__(strip_threads(NW), 1) k_fusion_strip(const Str
                 full_par ^= 1u << r;
                 tc::fence_after_sync();
                 const uint64_t da = dA0 + r * kSlotStep;
-                tc::mma_bf16(tmem_acc, dab, dwb, idesc, 0u);
+                if (!(p.debug & 1)) tc::mma_bf16(tmem_acc, dab, dwb, idesc, 0u);
 #pragma unroll
                 for (int kk = 0; kk < C / 16; ++kk) {
+                    if (p.debug & 1) break;
                     const uint64_t koff = kk * 16;   // 16 bf16 = two 16-byte k-units = 256 bytes
                     tc::mma_bf16(tmem_acc, da + koff, dw + koff, idesc, 1u);
                     if (NS == 2) {
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(strip_threads(NW), 1) k_fusion_strip(const Str
 #pragma unroll
                     for (int j = 0; j < G; ++j) {
                         if (j < ns) {
-                            const int32_t pr = (int32_t)tc::lds_u32(ibase + j * 4);
+                            const int32_t pr = (p.debug & 2) ? -1 : (int32_t)tc::lds_u32(ibase + j * 4);
                             const float *src = pr >= 0 ? Tb + (size_t)pr * C : g_strip_neg_row + u4 * 8;
 #pragma unroll
                             for (int it = 0; it < kItems; ++it) tc::ldg_nc_f32x8(src + it * 32, tv[j][rg * kItems + it]);
@@ -775,7 +778,7 @@ __global__ void __launch_bounds__(strip_threads(NW), 1) k_fusion_strip(const Str
                 for (int j = 0; j < G; ++j) {
                     if (j < ns) {
                         acquire();
-                        if (brow < rows) build(tv[j], sA + r * L::kASlot, rows);
+                        if (brow < rows && !(p.debug & 4)) build(tv[j], sA + r * L::kASlot, rows);
                         publish();
                     }
                 }
@@ -798,7 +801,7 @@ __global__ void __launch_bounds__(strip_threads(NW), 1) k_fusion_strip(const Str
                 mbar_wait_g(sBar + (kBarL3 + par) * 8, (l3_par >> par) & 1u, "layer 3 done (worker)");
                 l3_par ^= 1u << par;
                 tc::fence_after_sync();
-                if (q * 32 < rows) {
+                if (q * 32 < rows && !(p.debug & 16)) {
                     uint32_t z[CS];
                     if constexpr (CS == 8) tmem_ld8x1(tmem_base + lane_off + kTmemL3 + par * C + col0, z);
                     else tmem_ld16x1(tmem_base + lane_off + kTmemL3 + par * C + col0, z);
@@ -830,7 +833,7 @@ __global__ void __launch_bounds__(strip_threads(NW), 1) k_fusion_strip(const Str
                 group_par ^= 1u << set;
                 tc::fence_after_sync();
                 const int nvp = erow < rows ? (int)lds_u8(sNv + (uint32_t)(slot * S + t * kTile + erow)) : 0;
-                if (q * 32 < rows) pool(tmem_base + lane_off + set * (G * C) + col0, k0, ns, nvp);
+                if (q * 32 < rows && !(p.debug & 8)) pool(tmem_base + lane_off + set * (G * C) + col0, k0, ns, nvp);
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(sBar + (kBarAccFree + set) * 8);
@@ -942,6 +945,8 @@ int fusion_strip(const float *d_bev, const float *d_T, const int32_t *d_knn, int
     p.B = B; p.N = N; p.W = W; p.K = K; p.Ci = Ci; p.cells = (int32_t)cells;
     p.x0 = x0; p.y0 = y0; p.dx = dx; p.dy = dy;
     p.inplace = d_out == d_bev;
+    static const int dbg = getenv("CF_STRIP_DEBUG") ? atoi(getenv("CF_STRIP_DEBUG")) : 0;
+    p.debug = dbg;
     const int NS = mode == CF_MODE_FP32 ? 2 : 1;
     int rc;
     if (C == 32) rc = NS == 2 ? launch_strip<32, 2, 256, 5, 5, CF_STRIP_NW32>(p, st) : launch_strip<32, 1, 256, 5, 5, CF_STRIP_NW32>(p, st);

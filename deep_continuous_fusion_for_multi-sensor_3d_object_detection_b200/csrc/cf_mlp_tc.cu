@@ -43,7 +43,7 @@ struct Tuning {
     int max_ctas = 0;             // CF_MAX_CTAS: cap on resident CTAs per SM of the persistent fused kernels
     bool debug_launch = false;    // CF_DEBUG_LAUNCH: print the launch shape
     bool no_skew = false;         // CF_NO_SKEW: never use the double-buffered kernel
-    bool no_strip = false;        // CF_NO_STRIP: never use the strip pipeline (cf_fusion_strip.cu)
+    bool strip = false;           // CF_STRIP: route C = 32 / 64 through the experimental strip pipeline (cf_fusion_strip.cu)
     long long compact_min_tiles = -1;   // CF_COMPACT_MIN_TILES
 };
 static const Tuning &tuning()
@@ -53,7 +53,7 @@ static const Tuning &tuning()
         if (const char *e = getenv("CF_MAX_CTAS")) v.max_ctas = atoi(e);
         v.debug_launch = getenv("CF_DEBUG_LAUNCH") != nullptr;
         v.no_skew = getenv("CF_NO_SKEW") != nullptr;
-        v.no_strip = getenv("CF_NO_STRIP") != nullptr;
+        v.strip = getenv("CF_STRIP") != nullptr;
         if (const char *e = getenv("CF_COMPACT_MIN_TILES")) v.compact_min_tiles = atoll(e);
         return v;
     }();
@@ -1695,8 +1695,10 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
         k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, (uint8_t *)d_workspace + (size_t)NS * C * C * 2);
         count_launches(2);
     }
-    // fine scales: the strip pipeline (bulk-copy engine for every BEV byte, no compaction pass)
-    if (!tuning().no_strip) {
+    // fine scales, opt-in (CF_STRIP=1): the strip pipeline -- every BEV byte through tensor-map TMA, no compaction pass.
+    // Bit-identical results; measured slower than the compacted-tile kernels below at BASELINE configs[1] (378 vs 266 us on
+    // scale 1: its strip buffers are held through a three-deep worker pipeline, profiles/README.md), so it is not the default.
+    if (tuning().strip) {
         const int rc = fusion_strip(d_bev, d_T, d_knn, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_b2, d_b3, d_out, mode, img2,
                                     img3, st);
         if (rc != CF_ERR_UNSUPPORTED) return rc;

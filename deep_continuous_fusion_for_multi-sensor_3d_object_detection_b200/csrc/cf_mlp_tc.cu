@@ -43,7 +43,7 @@ struct Tuning {
     int max_ctas = 0;             // CF_MAX_CTAS: cap on resident CTAs per SM of the persistent fused kernels
     bool debug_launch = false;    // CF_DEBUG_LAUNCH: print the launch shape
     bool no_skew = false;         // CF_NO_SKEW: never use the double-buffered kernel
-    bool strip = false;           // CF_STRIP: route C = 32 / 64 through the experimental strip pipeline (cf_fusion_strip.cu)
+    bool seg = false;             // CF_SEG: route the fine scales through the segment-tile kernel (cf_fusion_seg.cu)
     long long compact_min_tiles = -1;   // CF_COMPACT_MIN_TILES
 };
 static const Tuning &tuning()
@@ -53,7 +53,7 @@ static const Tuning &tuning()
         if (const char *e = getenv("CF_MAX_CTAS")) v.max_ctas = atoi(e);
         v.debug_launch = getenv("CF_DEBUG_LAUNCH") != nullptr;
         v.no_skew = getenv("CF_NO_SKEW") != nullptr;
-        v.strip = getenv("CF_STRIP") != nullptr;
+        v.seg = getenv("CF_SEG") != nullptr;
         if (const char *e = getenv("CF_COMPACT_MIN_TILES")) v.compact_min_tiles = atoll(e);
         return v;
     }();
@@ -1641,10 +1641,9 @@ int launch_sk(const TcParams &p, cudaStream_t st)
 
 }  // namespace
 
-int fusion_strip(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H,
-                 int32_t W, int32_t K, float x0, float y0, float dx, float dy, const float *d_W1, int32_t Ci,
-                 const float *d_b2, const float *d_b3, float *d_out, int32_t mode, const uint8_t *img2, const uint8_t *img3,
-                 cudaStream_t st);
+int fusion_seg(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_t B, int32_t N, int32_t C, int32_t H, int32_t W,
+               int32_t K, float x0, float y0, float dx, float dy, const float *d_W1, int32_t Ci, const float *d_b2, const float *d_b3,
+               float *d_out, int32_t mode, const uint8_t *img2, const uint8_t *img3, void *d_ws, cudaStream_t st);
 
 static size_t tc_weight_bytes(int32_t C, int NS) { return ((size_t)2 * NS * C * C * 2 + 255) / 256 * 256; }
 
@@ -1695,15 +1694,14 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
         k_pack_weights<<<pack_blocks, 256, 0, st>>>(d_W3, C, C, C, KC, NS, (uint8_t *)d_workspace + (size_t)NS * C * C * 2);
         count_launches(2);
     }
-    // fine scales, opt-in (CF_STRIP=1): the strip pipeline -- every BEV byte through tensor-map TMA, no compaction pass.
-    // Bit-identical results; measured slower than the compacted-tile kernels below at BASELINE configs[1] (378 vs 266 us on
-    // scale 1: its strip buffers are held through a three-deep worker pipeline, profiles/README.md), so it is not the default.
-    if (tuning().strip) {
-        const int rc = fusion_strip(d_bev, d_T, d_knn, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_b2, d_b3, d_out, mode, img2,
-                                    img3, st);
+    const bool compact = ceil_div64(n_cells, kTile) * B >= min_tiles;
+    // fine scales (many more tiles than SMs): segment tiles, all neighbour slots in one MMA batch (cf_fusion_seg.cu); its
+    // lists live where the cell lists of the kernels below would
+    if (compact && tuning().seg) {
+        const int rc = fusion_seg(d_bev, d_T, d_knn, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_b2, d_b3, d_out, mode, img2,
+                                  img3, cell_count, st);
         if (rc != CF_ERR_UNSUPPORTED) return rc;
     }
-    const bool compact = ceil_div64(n_cells, kTile) * B >= min_tiles;
     if (compact) {
         CF_TRY(cuda_status(cudaMemsetAsync(cell_count, 0, 512, st), "cf_fusion_fwd memset"));
         k_cell_compact<<<dim3((unsigned)ceil_div64(n_cells, 256), (unsigned)B), 256, 0, st>>>(d_knn, K, n_cells, cell_list,

@@ -52,6 +52,23 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         : "memory");
 }
 
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  Guarding the tcgen05.mma / commit sequence with
+// `warp == w && elect_one()` instead of `tid == 0` lets ptxas keep descriptors in uniform registers and emit the UTCHMMAs
+// back to back; under a plain thread-index test it wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (~70 cycles per MMA,
+// measured: 15 % of the segment kernel's tile time went into issuing 35 small MMAs).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // all previously issued tcgen05 async ops of this thread arrive (count 1) on the mbarrier when complete
 __device__ __forceinline__ void commit(uint64_t *bar)
 {

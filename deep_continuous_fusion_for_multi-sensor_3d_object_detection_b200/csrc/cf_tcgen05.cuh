@@ -114,6 +114,65 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+
+// ---- TMA (cp.async.bulk.tensor) through a 2-D tensor map, completion on an mbarrier / bulk groups ---------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_addr, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// non-blocking probe (mbarrier.test_wait returns at once; try_wait may suspend the thread for a system-dependent time)
+__device__ __forceinline__ bool mbar_poll(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    while (!mbar_test(bar_addr, parity)) {
+    }
+}
+// box (x = fastest coordinate, y) of the tensor behind `tmap` -> shared memory; complete_tx on the mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar_addr)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(x), "r"(y), "r"(bar_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int32_t x, int32_t y, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- TMEM ---------------------------------------------------------------------------------------------------
 // one full warp; writes the base address to *dst (shared memory).  ncols: power of two in [32, 512]
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst, uint32_t ncols)
@@ -240,6 +299,15 @@ __device__ __forceinline__ void ldg_nc_f32x8(const float *p, float *v)
     asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
         : "l"(p));
+}
+
+// the same load pinned in program order (volatile asm): keeps a software-pipelined gather where it was written instead of
+// letting the scheduler hoist every load of a tile to its top (register pressure)
+__device__ __forceinline__ void ldg_nc_f32x8_pinned(const float *p, float *v)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
 }
 
 // 256-bit global store (sm_100: STG.E.256): a full 32-byte sector per lane, 32-byte aligned

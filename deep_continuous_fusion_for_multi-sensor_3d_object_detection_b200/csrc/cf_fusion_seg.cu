@@ -571,6 +571,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fusion_seg(const SegParams p, c
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+}  // namespace
+
 // 2-D tensor map over the channel planes of a (B, C, H, W) fp32 map: x = cell (fastest), y = b * C + c; box = 32 cells x rows
 int make_plane_map(CUtensorMap *tm, const float *base, int64_t cells, int64_t planes, int box_rows)
 {
@@ -591,6 +593,8 @@ int make_plane_map(CUtensorMap *tm, const float *base, int64_t cells, int64_t pl
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_LAUNCH, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return CF_OK;
 }
+
+namespace {
 
 template <int C, int NS, int G>
 int launch_seg(const SegParams &p, const CUtensorMap &tm_bev, const CUtensorMap &tm_out, int64_t tiles_max, cudaStream_t st)

@@ -11,6 +11,7 @@ from ._lib import SO_PATH, build, load  # noqa: F401
 from .fusion import ContinuousFusion, FrameContext, FusionRunner, fuse_scales, prepare_frames  # noqa: F401
 from .postprocess import PostProcess  # noqa: F401
 from .model import ObjectDetection_DCF  # noqa: F401
+from .loss import LossTotal  # noqa: F401
 
-__all__ = ["ContinuousFusion", "FrameContext", "FusionRunner", "fuse_scales", "prepare_frames", "PostProcess", "ObjectDetection_DCF", "geometry",
+__all__ = ["ContinuousFusion", "FrameContext", "FusionRunner", "fuse_scales", "prepare_frames", "PostProcess", "ObjectDetection_DCF", "LossTotal", "geometry",
            "synthetic", "build", "load", "SO_PATH"]

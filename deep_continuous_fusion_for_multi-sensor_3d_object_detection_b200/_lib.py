@@ -49,6 +49,8 @@ SIGNATURES = {
     "cf_voxelize_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cf_voxelize_project": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _i32, _i32, _i32,
                                       C.POINTER(C.c_float), _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cf_loss_targets": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _i32,
+                                  _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cf_get_bboxes": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
     "cf_nms_workspace_bytes": (_sz, [_i32, _i32]),
     "cf_nms_sat": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),

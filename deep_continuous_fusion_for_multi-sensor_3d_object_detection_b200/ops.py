@@ -386,6 +386,35 @@ def point_gather_bwd(grad_feat, img_like, points, num_points, calib=None, uv=Non
 
 
 # ------------------------------------------------------------------------------------------ post-process
+def loss_targets(ref_boxes, num_ref, H, W, scales, reduced_scale, positive_range, regress_type, pos_threshold, neg_threshold,
+                 shuffle_keys, candidates):
+    """LossTotal's target assignment (loss.py:74-127) for the whole batch in one launch.
+    ref_boxes (B,M,>=2) fp32, num_ref (B) int; scales = (x_scale, y_scale, x_offset, y_offset) of loss.py:80-83;
+    shuffle_keys (B, M*R*R) fp32 and candidates (B,L,2) int32 are the random draws (RNG contract: include/cf_b200.h).
+    Returns pos_cells (B,pos_threshold), pos_count (B), neg_cells (B,neg_threshold+1), neg_count (B), reg_cells (B,M,R*R):
+    int32 linear cells x*W+y, -1 padded."""
+    ref_boxes = _contig(ref_boxes, "ref_boxes", torch.float32, 3)
+    B, M, stride = ref_boxes.shape
+    num_ref = as_counts(num_ref, B, ref_boxes.device)
+    R = int(positive_range)
+    shuffle_keys = _contig(shuffle_keys, "shuffle_keys", torch.float32, 2)
+    candidates = _contig(candidates, "candidates", torch.int32, 3)
+    if tuple(shuffle_keys.shape) != (B, M * R * R) or candidates.shape[0] != B or candidates.shape[2] != 2:
+        raise ValueError("loss_targets: shuffle_keys must be (B, M*R*R), candidates (B, L, 2)")
+    dev = ref_boxes.device
+    pos = torch.empty((B, int(pos_threshold)), dtype=torch.int32, device=dev)
+    neg = torch.empty((B, int(neg_threshold) + 1), dtype=torch.int32, device=dev)
+    npos = torch.empty((B,), dtype=torch.int32, device=dev)
+    nneg = torch.empty((B,), dtype=torch.int32, device=dev)
+    reg = torch.empty((B, M, R * R), dtype=torch.int32, device=dev)
+    xs, ys, xo, yo = (float(v) for v in scales)
+    check(load().cf_loss_targets(ptr(ref_boxes), ptr(num_ref), B, M, stride, int(H), int(W), xs, ys, xo, yo, float(reduced_scale), R,
+                                 int(regress_type), int(pos_threshold), int(neg_threshold), ptr(shuffle_keys), ptr(candidates),
+                                 int(candidates.shape[1]), ptr(pos), ptr(npos), ptr(neg), ptr(nneg), ptr(reg), stream_ptr()),
+          "cf_loss_targets")
+    return pos, npos, neg, nneg, reg
+
+
 def get_bboxes(pred_cls, pred_box, thr=0.8, cap=4096):
     """P-1.  (B,4,H,W), (B,14,H,W) -> boxes (B,cap,7), counts (B,) i32 (clamped), counts_raw (B,) i32."""
     lib = load()

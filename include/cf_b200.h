@@ -190,6 +190,28 @@ CF_API int cf_voxelize_project(const float *d_raw, const int64_t *d_num_raw, int
                         float *d_points, float *d_uv, int64_t *d_num_points, void *d_workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SURVEY 8(f-4)  target assignment of LossTotal on device: getPositionOfPositive (loss.py:74-110) and
+ * getPositionOfNegative (loss.py:112-127) for every frame of the batch, no host loop and no host list.
+ *   d_ref_boxes (B,M,ref_stride) fp32 = object_data (x at [0], y at [1]); d_num_ref (B) int64
+ *   centre cell: int((x*x_scale + x_offset)/reduced_scale), int((y*y_scale + y_offset)/reduced_scale) in
+ *   fp32, truncated toward zero (loss.py:86-87); window positive_range^2 clipped to the (H,W) map.
+ *   RNG contract (the caller supplies the draws, so the reference run with the same draws can be compared):
+ *     d_shuffle_keys (B, M*R*R) fp32: the positive list of length n is reordered by the stable ascending
+ *       order of its first n keys (stands for np.random.shuffle, loss.py:106), then cut to pos_threshold;
+ *     d_candidates (B,L,2) int32: the (x,y) draws of the rejection loop (loss.py:116-126) in order; the
+ *       first neg_threshold+1 that are not in the cut positive list are kept.
+ *   out: d_pos_cells (B,pos_threshold) / d_neg_cells (B,neg_threshold+1) int32 linear cells x*W+y, -1 padded;
+ *        d_pos_count / d_neg_count (B) int32; d_reg_cells (B,M,R*R) int32: the regression cells of every box
+ *        in window order (whole window for regress_type 0, centre only otherwise), -1 = none.
+ * ------------------------------------------------------------------------------------------- */
+CF_API int cf_loss_targets(const float *d_ref_boxes, const int64_t *d_num_ref, int32_t B, int32_t M, int32_t ref_stride,
+                    int32_t H, int32_t W, float x_scale, float y_scale, float x_offset, float y_offset,
+                    float reduced_scale, int32_t positive_range, int32_t regress_type, int32_t pos_threshold,
+                    int32_t neg_threshold, const float *d_shuffle_keys, const int32_t *d_candidates, int32_t L,
+                    int32_t *d_pos_cells, int32_t *d_pos_count, int32_t *d_neg_cells, int32_t *d_neg_count,
+                    int32_t *d_reg_cells, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * P-1  Test.get_bboxes (test.py:88-108) on device: per frame, anchor 0 then anchor 1, cells in
  * row-major order with cls[b,2a+1] > thr; gathers the 7 decoded channels [7a,7a+7).
  *   d_pred_cls (B,4,H,W), d_pred_box (B,14,H,W) fp32; d_boxes (B,cap,7) out; d_counts (B) int32 out

@@ -72,6 +72,42 @@ def chain_fixture():
     np.savez_compressed(os.path.join(OUT, "postprocess_chain.npz"), **data)
 
 
+def loss_fixture(regress_type, seed):
+    """LossTotal (loss.py:33-189) of the unmodified reference on a seeded batch: boxes inside, on the border and outside the
+    map, overlapping windows, a frame with the maximum of 20 boxes (more positives than the 128 kept) and one with 2."""
+    cfg = dcf_b200.geometry.carla_config(regress_type=regress_type)
+    rng = np.random.default_rng(seed)
+    B, M, H, W = 4, 20, 96, 64
+    ref = np.zeros((B, M, 8), np.float32)
+    num = np.array([6, 20, 2, 11], np.int64)
+    for b in range(B):
+        n = int(num[b])
+        ref[b, :n, 0] = rng.uniform(-3, 74, n)      # a few centres fall outside 0..70 m / -30..30 m
+        ref[b, :n, 1] = rng.uniform(-33, 33, n)
+        ref[b, :n, 2] = rng.uniform(-2, -1, n)
+        ref[b, :n, 3:6] = np.array([4, 2, 1.5]) * np.exp(0.1 * rng.normal(size=(n, 3)))
+        ref[b, :n, 6] = rng.uniform(-math.pi, math.pi, n)
+        ref[b, :n, 7] = 1
+    ref[3, 0, :2] = (0.1, -29.9)                    # corner cell: the window is clipped on two sides
+    ref[3, 1, :2] = (0.5, -29.5)                    # overlaps the window of box 0
+    ref[3, 2, :2] = (-0.1, 0.0)                     # int() truncates -0.125 to cell 0: counted as inside (loss.py:86,88)
+    pred_cls = rng.normal(size=(B, 4, H, W)).astype(np.float32)
+    pred_reg = (0.3 * rng.normal(size=(B, 14, H, W))).astype(np.float32)
+    R_ = cfg["positive_range"]
+    L = 4 * (cfg["neg_sample_threshold"] + 1)
+    keys = rng.random((B, M * R_ * R_)).astype(np.float32)
+    cand = np.stack([rng.integers(0, H, (B, L)), rng.integers(0, W, (B, L))], axis=2).astype(np.int32)
+    losses, pos, neg = R.loss_total(cfg, ref, num, pred_cls, pred_reg, keys, cand)
+    pos_a = -np.ones((B, cfg["pos_sample_threshold"]), np.int32)
+    neg_a = -np.ones((B, cfg["neg_sample_threshold"] + 1), np.int32)
+    for b in range(B):
+        pos_a[b, :len(pos[b])] = pos[b]
+        neg_a[b, :len(neg[b])] = neg[b]
+    return dict(ref=ref, num=num, pred_cls=pred_cls, pred_reg=pred_reg, keys=keys, cand=cand, losses=losses, pos=pos_a,
+                npos=np.array([len(x) for x in pos], np.int32), neg=neg_a, nneg=np.array([len(x) for x in neg], np.int32),
+                regress_type=np.int32(regress_type))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = R.load()
@@ -173,6 +209,12 @@ def main():
                             vox_idx=nzi, vox_val=vox.ravel()[nzi], pointcloud_raw=pc.numpy()[:num + 8],
                             projected_loc_uv=uv.numpy()[:num + 8], num_points_raw=np.int64(num), crt=ds.CRT_tensor.numpy())
         print("voxelize", tag, raw.shape[0], "->", num, "nonzero voxels", nzi.size)
+
+    # ---- LossTotal (loss.py:33-189): target lists and per-frame values of the unmodified reference, both regress types
+    for rt, seed in ((0, 19), (1, 20)):
+        fx = loss_fixture(rt, seed)
+        np.savez_compressed(os.path.join(OUT, f"loss_total_rt{rt}.npz"), **fx)
+        print("loss_total regress_type", rt, "losses", fx["losses"], "positives", fx["npos"], "negatives", fx["nneg"])
 
 
 if __name__ == "__main__":

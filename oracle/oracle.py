@@ -313,3 +313,89 @@ def voxelize_project(raw, config, crt):
     pc[:num] = pts[s2][c2]
     uvp[:num] = uv2.T[c2]
     return vox, pc, uvp, num
+
+
+# ---- target assignment and value of LossTotal (loss.py:33-189), restated with explicit random draws -----
+def loss_targets(ref_boxes, num_ref, H, W, scales, reduced_scale, positive_range, regress_type, pos_thr, neg_thr, keys, cand):
+    """getPositionOfPositive (loss.py:74-110) + getPositionOfNegative (loss.py:112-127) for every frame, plain loops.
+    RNG contract (include/cf_b200.h, cf_loss_targets): np.random.shuffle(list) == list[stable argsort(keys[:len(list)])],
+    the rejection loop's (x, y) draws are cand[b] in order.  Returns pos (B,pos_thr), npos (B), neg (B,neg_thr+1), nneg (B),
+    reg (B,M,R*R): int32 linear cells x*W+y, -1 padded."""
+    ref_boxes = np.asarray(ref_boxes, dtype=np.float32)
+    B, M, _ = ref_boxes.shape
+    R = int(positive_range)
+    xs, ys, xo, yo = (np.float32(v) for v in scales)
+    rs = np.float32(reduced_scale)
+    pos = -np.ones((B, pos_thr), np.int32)
+    neg = -np.ones((B, neg_thr + 1), np.int32)
+    reg = -np.ones((B, M, R * R), np.int32)
+    npos, nneg = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    for b in range(B):
+        plist = []
+        for i in range(int(num_ref[b])):
+            # loss.py:86-87: float32 tensor arithmetic, int() truncates toward zero
+            px = int(np.float32(np.float32(ref_boxes[b, i, 0] * xs) + xo) / rs)
+            py = int(np.float32(np.float32(ref_boxes[b, i, 1] * ys) + yo) / rs)
+            if px < 0 or px > H - 1 or py < 0 or py > W - 1:
+                continue
+            for xi in range(R):
+                x = px - int(R / 2) + xi
+                for yi in range(R):
+                    y = py - int(R / 2) + yi
+                    if x < 0 or x > H - 1 or y < 0 or y > W - 1:
+                        continue
+                    plist.append(x * W + y)
+                    if regress_type == 0 or (x == px and y == py):
+                        reg[b, i, xi * R + yi] = x * W + y
+        order = np.argsort(np.asarray(keys[b][:len(plist)], dtype=np.float32), kind="stable")
+        plist = [plist[j] for j in order][:pos_thr]
+        npos[b] = len(plist)
+        pos[b, :len(plist)] = plist
+        taken = set(plist)
+        k = 0
+        for x, y in np.asarray(cand[b]):
+            if int(x) * W + int(y) in taken:
+                continue
+            neg[b, k] = int(x) * W + int(y)
+            k += 1
+            if k > neg_thr:
+                break
+        nneg[b] = k
+    return pos, npos, neg, nneg, reg
+
+
+def loss_per_frame(ref_boxes, num_ref, pred_cls, pred_reg, anchors, targets, gain):
+    """Value of LossTotal for every frame (loss.py:52-71, 129-189) from the assigned targets, frame by frame and box by
+    box with torch CPU ops as the reference does (CrossEntropyLoss mean, SmoothL1Loss none); float32."""
+    import torch
+    import torch.nn.functional as F
+    pos, npos, neg, nneg, reg = targets
+    pred_cls, pred_reg = torch.as_tensor(pred_cls), torch.as_tensor(pred_reg)
+    anchors = torch.as_tensor(anchors)                     # (14, H, W)
+    ref_boxes = torch.as_tensor(np.asarray(ref_boxes, dtype=np.float32))
+    B, _, H, W = pred_cls.shape
+    out = []
+    for b in range(B):
+        pc, ng = torch.as_tensor(pos[b, :npos[b]]).long(), torch.as_tensor(neg[b, :nneg[b]]).long()
+        total = torch.zeros(())
+        for a in range(2):                                 # loss.py:62-63: channels [:2] and [2:4]
+            logits = pred_cls[b, 2 * a:2 * a + 2].reshape(2, H * W)
+            total = total + F.cross_entropy(logits[:, ng].T, torch.zeros(len(ng), dtype=torch.long))
+            if len(pc):
+                total = total + F.cross_entropy(logits[:, pc].T, torch.ones(len(pc), dtype=torch.long))
+        regl = torch.zeros(())
+        for i in range(int(num_ref[b])):
+            cells = torch.as_tensor(reg[b, i][reg[b, i] >= 0]).long()
+            if len(cells) == 0:
+                continue
+            p = pred_reg[b].reshape(14, H * W)[:, cells].T.reshape(-1, 2, 7)
+            an = anchors.reshape(2, 7, H * W)[:, :, cells].permute(2, 0, 1)
+            r = ref_boxes[b, i][None, None, :].expand(len(cells), 2, -1)
+            xy = (r[..., :2] - an[..., :2]) / torch.sqrt(an[..., 3:4] ** 2 + an[..., 4:5] ** 2)
+            z = (r[..., 2:3] - an[..., 2:3]) / an[..., 5:6]
+            whd = torch.log(r[..., 3:6] / an[..., 3:6])
+            d = r[..., 6] - an[..., 6]
+            tgt = torch.cat((xy, z, whd, torch.atan2(torch.sin(d), torch.cos(d))[..., None]), dim=-1)
+            regl = regl + F.smooth_l1_loss(p, tgt, reduction="none").sum() / (len(cells) * 14)
+        out.append(float(total + gain * regl))
+    return np.asarray(out, dtype=np.float64)

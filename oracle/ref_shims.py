@@ -116,3 +116,79 @@ def carla_dataset_stub(config):
     ds.pc_to_voxel_indice = torch.tensor([[x_scale, 0, 0, x_offset], [0, y_scale, 0, y_offset],
                                           [0, 0, z_scale, z_offset]], dtype=torch.float).permute(1, 0)
     return ds
+
+
+def loss_total(config, ref_boxes, num_ref, pred_cls, pred_reg, keys, cand):
+    """The reference's LossTotal (loss.py:33-189), UNMODIFIED, run on the CPU for every frame of the batch with the random
+    draws of the RNG contract (oracle.loss_targets).  Harness-side stubs only: torchvision (loss.py:3 imports save_image
+    for a __main__ block), Tensor.cuda -> identity (loss.py:40,51 call .cuda() unconditionally; the container has no GPU),
+    np.random.shuffle / randint -> the supplied draws.  loss.py:71 keeps only the LAST frame of a batch, so frame b's value
+    is obtained by calling the reference on the batch cut after frame b.
+    Returns (losses (B,), positives per frame, negatives per frame) -- the lists are the reference's own, captured from
+    getPositionOfPositive / getPositionOfNegative."""
+    import contextlib
+    import numpy as np
+    import torch
+    load()
+    for name in ("torchvision", "torchvision.utils"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["torchvision.utils"].save_image = lambda *a, **k: None
+    sys.modules["torchvision"].utils = sys.modules["torchvision.utils"]
+    saved_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    sys.path.insert(0, REFERENCE_DIR)
+    try:
+        loss_mod = importlib.import_module("loss")
+        state = {"frame": -1, "c": 0}
+        W = pred_cls.shape[3]
+
+        def shuffle(lst):
+            state["frame"] += 1
+            state["c"] = 0
+            order = np.argsort(np.asarray(keys[state["frame"]][:len(lst)], dtype=np.float32), kind="stable")
+            lst[:] = [lst[j] for j in order]
+
+        def randint(n):
+            b, c = state["frame"], state["c"]
+            state["c"] += 1
+            return int(cand[b][c // 2][c % 2])
+
+        captured = {"pos": [], "neg": []}
+        LT = loss_mod.LossTotal
+        orig_pos, orig_neg = LT.getPositionOfPositive, LT.getPositionOfNegative
+
+        def cap_pos(self, *a, **k):
+            r = orig_pos(self, *a, **k)
+            captured["pos"].append([p[0] * W + p[1] for p in r[2]])
+            return r
+
+        def cap_neg(self, *a, **k):
+            r = orig_neg(self, *a, **k)
+            captured["neg"].append([p[0] * W + p[1] for p in r])
+            return r
+
+        saved = np.random.shuffle, np.random.randint
+        np.random.shuffle, np.random.randint = shuffle, randint
+        LT.getPositionOfPositive, LT.getPositionOfNegative = cap_pos, cap_neg
+        try:
+            lt = LT(config)
+            B = ref_boxes.shape[0]
+            losses, pos, neg = [], [], []
+            with torch.no_grad():
+                for b in range(B):
+                    state["frame"] = -1
+                    captured["pos"].clear()
+                    captured["neg"].clear()
+                    v = lt(torch.as_tensor(ref_boxes[:b + 1]), torch.as_tensor(num_ref[:b + 1]), torch.as_tensor(pred_cls[:b + 1]),
+                           torch.as_tensor(pred_reg[:b + 1]))
+                    losses.append(float(v))
+                    pos.append(list(captured["pos"][-1]))
+                    neg.append(list(captured["neg"][-1]))
+        finally:
+            np.random.shuffle, np.random.randint = saved
+            LT.getPositionOfPositive, LT.getPositionOfNegative = orig_pos, orig_neg
+    finally:
+        torch.Tensor.cuda = saved_cuda
+        sys.path.remove(REFERENCE_DIR)
+    return np.asarray(losses), pos, neg

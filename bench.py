@@ -690,6 +690,32 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args):
+    """BASELINE.json configs[3] under the bench contract: the full train step of the drop-in model (LiDAR backbone + camera
+    trunk + continuous fusion at every residual group + LossTotal with device-side target assignment, forward + backward +
+    Adam), batch-partitioned over the ranks with DDP's gradient all-reduce over NCCL (the path's only collective).
+    `--impl reference`: the reference has no fusion layer and its train.py needs a private dataset, so there is nothing to run."""
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "train.py of the reference needs its private CARLA dataset and has no fusion layer"}), flush=True)
+        return
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import train_step_bench
+    argv = ["--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))]
+    if not args.no_graph and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        argv.append("--graph")
+    res = train_step_bench.main(argv)
+    if res is None:
+        return
+    line = {"metric": "train_step_frames_per_sec", "value": res["frames_per_sec"], "unit": UNIT, "n_gpus": res["n_gpus"],
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train: BASELINE.json configs[3] (ObjectDetection_DCF on the reference YAML grid 384x256, batch 4/GPU, "
+                                   "fusion at all five groups K=3, LossTotal, Adam; DDP all-reduce over NCCL for N > 1)"},
+            "run": {k: res[k] for k in ("launch", "loss", "host_enqueue_ms_per_step", "loss_value")}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -704,7 +730,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--bucket-size", type=float, default=None, help="K-1 bucket pitch in metres (default: config)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "train":
+        run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[4]: throughput sweep over the batch size on one GPU -- the fusion hot path of configs[1]
-(K=5, five scales of a 700x800 BEV, fp32 mode) plus the greedy SAT NMS on 2 000 boxes per frame.
-Frames of the 4-frame synthetic workload are repeated to fill larger batches (frames are independent).
-Prints one JSON line per batch size; not part of the bench contract."""
+"""BASELINE.json configs[4]: throughput sweep over the batch size -- the fusion hot path of configs[1] (K=5, five scales of a
+700x800 BEV, fp32 mode) plus the greedy SAT NMS on 2 000 boxes per frame.  One GPU, or `torchrun --nproc-per-node N`: every
+rank runs its own batch of that size (frames are independent, no collective on the path), the step time is the maximum over
+the ranks and the rate the aggregate.  Frames of the 4-frame synthetic workload are repeated to fill larger batches.
+Prints one JSON line per batch size on rank 0; not part of the bench contract."""
 import argparse
 import json
 import os
@@ -20,8 +21,11 @@ def main():
     ap.add_argument("--batches", default="1,2,4,8,16,32,64")
     ap.add_argument("--steps", type=int, default=10)
     a = ap.parse_args()
-    dev = torch.device("cuda")
-    wl = dcf.synthetic.make_workload("cfg1", seed=100)
+    rank, world, local = dcf.dist_util.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dcf.dist_util.init("nccl", dev)
+    wl = dcf.synthetic.make_workload("cfg1", seed=dcf.dist_util.rank_seed(100, rank))
     mode = wl["workload"]["mode"]
     to = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     base = {"points": to(wl["points"]), "counts": to(wl["num_points"]), "img": to(wl["img_feat"]),
@@ -61,18 +65,24 @@ def main():
             step()
         for _ in range(3):
             graph.replay()
+        dcf.dist_util.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.steps):
             graph.replay()
         e1.record()
+        dcf.dist_util.barrier()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / a.steps
-        print(json.dumps({"batch": B, "ms_per_step": round(ms, 4), "frames_per_sec": round(B / ms * 1e3, 1),
-                          "includes": "fusion (5 scales, fp32 mode, out of place) + SAT NMS on 2000 boxes/frame", "launch": "cuda_graph_replay"}), flush=True)
+        ms = dcf.dist_util.max_over_ranks([e0.elapsed_time(e1) / a.steps], device=dev)[0]
+        if rank == 0:
+            print(json.dumps({"batch_per_gpu": B, "n_gpus": world, "ms_per_step": round(ms, 4), "frames_per_sec": round(B * world / ms * 1e3, 1),
+                              "includes": "fusion (5 scales, fp32 mode, out of place) + SAT NMS on 2000 boxes/frame",
+                              "launch": "cuda_graph_replay"}), flush=True)
         del graph, pts, cnt, img, bevs, boxes
         torch.cuda.empty_cache()
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -313,6 +313,18 @@ def run_gpu(args):
     device = torch.device("cuda", local)
     import torch.distributed as dist
     dcf.dist_util.init("nccl", device)
+    # N ranks share one host: give every rank its own slice of the cores, so that its launch thread and its pinned-buffer
+    # traffic do not migrate between the ranks' cores (the end-to-end arm is bound by the host side at N > 1)
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            affinity = [mine[0], mine[-1]]
+        except OSError:
+            affinity = None
 
     def barrier():
         dcf.dist_util.barrier()
@@ -425,9 +437,35 @@ def run_gpu(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    # the two PCIe directions on their own (same pinned buffers, same per-frame copies): what one rank's link gives when the
+    # other direction is idle; with N ranks on one host the ratio to the N = 1 figure is the host-side ceiling
+    def copy_rate(direction):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            for f in range(B):
+                r = runners[f % 2]
+                if direction == "h2d":
+                    r.points.copy_(h_points[f:f + 1], non_blocking=True)
+                    r.img_feat.copy_(h_img[f:f + 1], non_blocking=True)
+                    for d, hb in zip(r.bevs, h_bev):
+                        d.copy_(hb[f:f + 1], non_blocking=True)
+                else:
+                    for o, h in zip(r.bevs, h_out):
+                        h[f:f + 1].copy_(o, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        return (h2d if direction == "h2d" else d2h) * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+    barrier()
+    h2d_gbs = copy_rate("h2d")
+    barrier()
+    d2h_gbs = copy_rate("d2h")
+    barrier()
 
     # ---- max over ranks ---------------------------------------------------------------------------------
-    ms, ms_e2e, ms_steady = dcf.dist_util.max_over_ranks([ms, ms_e2e, ms_steady], device=device)
+    ms, ms_e2e, ms_steady, inv_h2d, inv_d2h = dcf.dist_util.max_over_ranks([ms, ms_e2e, ms_steady, 1.0 / h2d_gbs, 1.0 / d2h_gbs], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -553,7 +591,10 @@ def run_gpu(args):
         "steady_200_replays": {"replays": n_steady, "ms_per_step": round(ms_steady / n_steady, 4),
                                "value": round(dcf.dist_util.aggregate_rate(B, world, n_steady, ms_steady), 2), "unit": UNIT},
         "e2e": {"value": round(dcf.dist_util.aggregate_rate(B, world, e2e_steps, ms_e2e), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 3),
+                "per_rank_gbs": {"h2d_alone_min_over_ranks": round(1.0 / inv_h2d, 1), "d2h_alone_min_over_ranks": round(1.0 / inv_d2h, 1),
+                                 "both_directions_in_e2e": round((h2d + d2h) / (ms_e2e / e2e_steps * 1e-3) / 1e9, 1)},
+                "host_affinity_cores_rank0": affinity},
         "gpu_launches": int(launches),
         "roofline": roof,
         "roofline_per_scale": {"tensor_peak_tflops": tpeak, "tensor_peak_source": tpeak_src, "hbm_peak_gbs": peak, "launches": per_scale},

@@ -336,6 +336,14 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     const uint32_t ab_row = sAb_addr + tc::unit_offset(row, 0, 2);
     constexpr uint32_t idesc = tc::make_idesc_bf16(kTile, C);
     uint32_t phase = 0, iter = 0;
+    // the thread that issues the MMAs (called by every thread right behind a CTA barrier).  Wide shapes (1 CTA per SM, spare
+    // registers): an elected lane of warp 0, so that ptxas keeps the descriptors in uniform registers and the 12 + MMAs of a chunk
+    // step go out back to back; under `tid == 0` every UTCHMMA sits in its own ELECT / BRA.U.ANY loop (~70 cycles each), which
+    // the narrow shapes accept because the elected form costs them registers (measured: spills, 266 -> 275 us at C = 32).
+    auto issuer = [&]() -> bool {
+        if constexpr (C >= 192) return warp == 0 && tc::elect_one();
+        else return tid == 0;
+    };
 
     // A-tile work split: a warp takes one 8-row group x 4 operand units (32 channels) per step, lane (r8 = lane % 8,
     // u = lane / 8).  Global side: the 4 lanes of a row read one contiguous 128-byte segment of the point's T row;
@@ -512,6 +520,19 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gather(Tc, neg, idx0 + i * kStep * 32, tv + 8 * i);
             }
+            // Chunked shapes (C > 128: a round is kChunks chunk steps of KC input channels): the neighbour rows of the NEXT
+            // chunk step are gathered into registers right after this step's MMAs are issued and are built after its wait --
+            // the L2 round trip of the gather (~1 us of a ~3 us chunk step) leaves the tile's chain.
+            constexpr bool kPipe2 = CF_PIPE && !kPipe && L::kChunks > 1;
+            constexpr int kMaxItems = (16 + kStep - 1) / kStep;
+            float pv[kPipe2 ? kMaxItems * 8 : 1];
+            auto gather_chunk = [&](int k, int ch) {
+                const float *Tc = Tb + ch * KC + ku * 8, *neg = g_neg_row + ch * KC + ku * 8;
+#pragma unroll
+                for (int m = 0; m < kMaxItems; ++m)
+                    if (rg0 + m * kStep < 16) gather(Tc, neg, idx0 + (uint32_t)(k * kTile * 4 + m * kStep * 32), pv + 8 * m);
+            };
+            if (kPipe2 && R > 0) gather_chunk(0, 0);
             if (R == 0) prefetch_bev();
 
             for (int k = 0; k < R; ++k) {
@@ -529,6 +550,15 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                             if (i < 3) ctr_next = tc::lds_f32x4(ctr0 + (i + 1) * kStep * 128);
                             build(tv + 8 * i, ctr, dst0 + i * kStep * kc_units * 128);
                             ctr = ctr_next;
+                        }
+                    } else if (kPipe2) {
+                        load_offset_weights(ch);
+#pragma unroll
+                        for (int m = 0; m < kMaxItems; ++m) {
+                            if (rg0 + m * kStep < 16) {
+                                const float4 cm = tc::lds_f32x4(ctr0 + m * kStep * 128);
+                                build(pv + 8 * m, cm, dst0 + m * kStep * kc_units * 128);
+                            }
                         }
                     } else {
                         load_offset_weights(ch);
@@ -551,7 +581,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     tc::fence_proxy_async();
                     tc::fence_before_sync();
                     __syncthreads();
-                    if (tid == 0) {
+                    if (issuer()) {
                         tc::fence_after_sync();
                         if (ch == 0)
                             tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr, 128, 256), idesc, 0u);
@@ -565,6 +595,10 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                                                                  : p.wimg3;
                         ++wn;
                         prefetch_wchunk(nsrc, wn & 1);   // its buffer was last read by the previous chunk's MMAs, already complete
+                    }
+                    if (kPipe2) {   // the next chunk step's rows: this round's next chunk, or the first chunk of the next round
+                        if (ch + 1 < L::kChunks) gather_chunk(k, ch + 1);
+                        else if (k + 1 < R) gather_chunk(k + 1, 0);
                     }
                     if (ch == L::kChunks - 1) {
                         // work that overlaps this round's MMA and epilogue: the next tile's header, then the next round's
@@ -635,7 +669,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     tc::fence_proxy_async();
                     tc::fence_before_sync();
                     __syncthreads();
-                    if (tid == 0) {
+                    if (issuer()) {
                         tc::fence_after_sync();
                         if (ch == 0)
                             tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr + L::kWbBytes, 128, 256),

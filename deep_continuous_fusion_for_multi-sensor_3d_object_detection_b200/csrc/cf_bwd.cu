@@ -507,7 +507,11 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     const int32_t *n_cells = w.counters, *n_rows = w.counters + 1;
     const unsigned cchunks = (unsigned)((C + 31) / 32), ctiles = (unsigned)((C + 63) / 64);
     const bool tc = mode != CF_MODE_FP32_SIMT && aligned16(d_gfeat) && aligned16(d_feat) && (!d_T || aligned16(d_T));
-    const bool tc_row_nn = tc && bwd_tc_nn_fits(C, C);    // [rows x C] x [C x C]: the weight image + one A chunk fit up to C = 128
+    // [rows x C] x [C x C]: the weight image + one A chunk fit in shared memory up to C = 192; at C = 256 the GEMM runs as two
+    // column halves (N = 128 each: 128 KB of weights + a 64 KB A chunk), every epilogue being local to its columns
+    const int nsp = bwd_tc_nn_fits(C, C) ? 1 : 2;
+    const int32_t Nh = C / nsp;
+    const bool tc_row_nn = tc && bwd_tc_nn_fits(C, Nh);
     const bool tc_row_tn = tc && bwd_tc_tn_fits(C, C);
     const bool tc_pt_nn = tc && bwd_tc_nn_fits(C, Ci);    // dF = dT W1
     const bool tc_pt_tn = tc && bwd_tc_tn_fits(C, Ci);    // dW1 | db1 = dT^T [F | P | 1]
@@ -535,17 +539,35 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
             Ws[n] = Wm; lds[n] = ld; Nns[n] = Nn; Kds[n] = Kd; trs[n] = tr; imgs[n] = img;
             ++n;
         };
+        const size_t half_bytes = (size_t)2 * Nh * C * 2;   // one column half's image (hi | lo)
+        auto flush = [&]() -> int {
+            const int rc = n ? bwd_tc_pack4(Ws, lds, Nns, Kds, trs, imgs, n, st) : CF_OK;
+            n = 0;
+            return rc;
+        };
         if (tc_row_nn) {
-            job(d_W2, C, C, C, 0, w.pW2);
-            job(d_W2, C, C, C, 1, w.pW2t);
-            job(d_W3, C, C, C, 1, w.pW3t);
+            for (int h = 0; h < nsp; ++h) {
+                // B = W (n = output row): rows [h Nh, +Nh);  B = W^T (n = column): columns [h Nh, +Nh)
+                job(d_W2 + (size_t)h * Nh * C, C, Nh, C, 0, (uint8_t *)w.pW2 + h * half_bytes);
+                job(d_W2 + (size_t)h * Nh, C, Nh, C, 1, (uint8_t *)w.pW2t + h * half_bytes);
+                job(d_W3 + (size_t)h * Nh, C, Nh, C, 1, (uint8_t *)w.pW3t + h * half_bytes);
+                if (h + 1 < nsp) CF_TRY(flush());
+            }
         }
         if (tc_pt_nn) job(d_W1, ldw1, Ci, C, 1, w.pW1t);
-        CF_TRY(bwd_tc_pack4(Ws, lds, Nns, Kds, trs, imgs, n, st));
+        CF_TRY(flush());
     }
+    // row-side NN GEMM, one launch per column half
+    auto row_nn = [&](const float *X, int64_t R, const int32_t *d_R, const void *img, float *Out, int epi, const float *aux, int64_t ldaux) -> int {
+        const size_t half_bytes = (size_t)2 * Nh * C * 2;
+        for (int h = 0; h < nsp; ++h)
+            CF_TRY(bwd_tc_gemm_nn(X, C, R, d_R, C, Nh, (const uint8_t *)img + h * half_bytes, Out + (size_t)h * Nh, C, epi,
+                                  aux ? aux + (size_t)h * Nh : nullptr, ldaux, st));
+        return CF_OK;
+    };
     if (tc_row_nn) {
         // H2 = relu(H1 W2^T + b2)
-        CF_TRY(bwd_tc_gemm_nn(w.H1, C, rows, n_rows, C, C, w.pW2, w.H2, C, EPI_BIAS_RELU, d_b2, 0, st));
+        CF_TRY(row_nn(w.H1, rows, n_rows, w.pW2, w.H2, EPI_BIAS_RELU, d_b2, 0));
     } else {
         k_transpose_sq_b<<<(C * C + 255) / 256, 256, 0, st>>>(d_W2, C, w.W2t);
         // Z2 = H1 W2^T  (as  H1 [rows x C] * W2t [C x C])
@@ -576,7 +598,7 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     }
     // dPooled = G W3   (W3 is (out, in) row-major: exactly the [K=out x N=in] operand)
     if (tc_row_nn) {
-        CF_TRY(bwd_tc_gemm_nn(w.G, C, ncell, n_cells, C, C, w.pW3t, w.dPooled, C, EPI_STORE, nullptr, 0, st));
+        CF_TRY(row_nn(w.G, ncell, n_cells, w.pW3t, w.dPooled, EPI_STORE, nullptr, 0));
     } else {
         k_sgemm_nn<<<dim3((unsigned)ceil_div64(ncell, 64), ctiles), 256, 0, st>>>(w.G, C, d_W3, C, w.dPooled, C, ncell, C, C, 0,
                                                                                  nullptr, 0, n_cells);
@@ -604,7 +626,7 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
     }
     // dA = (dZ2 W2) * [H1 > 0]   written over H1 (the mask is read before the overwrite, element by element)
     if (tc_row_nn) {
-        CF_TRY(bwd_tc_gemm_nn(w.H2, C, rows, n_rows, C, C, w.pW2t, w.H1, C, EPI_MASK, w.H1, C, st));
+        CF_TRY(row_nn(w.H2, rows, n_rows, w.pW2t, w.H1, EPI_MASK, w.H1, C));
     } else {
         k_sgemm_nn<<<dim3((unsigned)ceil_div64(rows, 64), ctiles), 256, 0, st>>>(w.H2, C, d_W2, C, w.H1, C, rows, C, C, 0, w.H1,
                                                                                 C, n_rows);

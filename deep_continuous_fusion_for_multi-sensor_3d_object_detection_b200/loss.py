@@ -108,6 +108,8 @@ class LossTotal(nn.Module):
     def per_frame(self, reference_bboxes_batch, num_ref_bbox_batch, pred_cls, pred_reg, draws=None):
         """(B,) loss of every frame: class terms of both lists + regress_loss_gain * regression term (loss.py:62-71)."""
         _, _, H, W = pred_cls.shape
+        # (the CARLA reader collates object_data as it finds it in the HDF5 file; the device path works on fp32 on the predictions' device)
+        reference_bboxes_batch = reference_bboxes_batch.to(device=pred_cls.device, dtype=torch.float32)
         pos, npos, neg, nneg, reg = self.targets(reference_bboxes_batch, num_ref_bbox_batch, H, W, draws)
         cls = self.class_term(pred_cls, pos, npos, 1) + self.class_term(pred_cls, neg, nneg, 0)
         return cls + self.gain * self.regress_term(pred_reg, reference_bboxes_batch.to(pred_reg.dtype), reg)

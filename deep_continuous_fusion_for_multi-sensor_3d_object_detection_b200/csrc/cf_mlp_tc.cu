@@ -140,8 +140,8 @@ struct TcLayout {
     static constexpr int kOffCtr = kOffWb + 2 * kWbBytes;           // float4 (cx,cx,cy,cy) [2][128]
     static constexpr int kOffCell = kOffCtr + 2 * kTile * 16;       // int32 cell of each row [2][128]
     static constexpr int kOffW1 = kOffCell + 2 * kTile * 4;         // float w1x[C], w1y[C]
-    static constexpr int kOffBar = kOffW1 + 2 * C * 4;              // mbarrier (8 B), tmem ptr (4 B), pad, int wmax[2][4]
-    static constexpr int kOffIdx = kOffBar + 48;                    // int32 [2][K][128] (K known at launch)
+    static constexpr int kOffBar = kOffW1 + 2 * C * 4;              // mbarrier (8 B), tmem ptr (4 B), pad, int wmax[2][4], weight-chunk mbarriers [2]
+    static constexpr int kOffIdx = kOffBar + 64;                    // int32 [2][K][128] (K known at launch)
     static __host__ __device__ constexpr int smem_bytes(int K) { return kOffIdx + 2 * K * kTile * 4; }
     static constexpr int kTmemCols = tmem_cols_for(2 * C);          // accumulator + the pooled sum
     static_assert(smem_bytes(CF_MAX_K) <= 227 * 1024, "layout exceeds the shared memory of an SM");
@@ -285,8 +285,11 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     const int64_t cells = (int64_t)p.H * p.W;
 
     // ---- one-time setup -----------------------------------------------------------------------------------------
+    const uint32_t wbar = tc::smem_u32(smem + L::kOffBar + 48);   // [2]: a streamed weight chunk has landed in its buffer
     if (tid == 0) {
         tc::mbar_init(bar, 1);
+        tc::mbar_init(reinterpret_cast<uint64_t *>(smem + L::kOffBar + 48), 1);
+        tc::mbar_init(reinterpret_cast<uint64_t *>(smem + L::kOffBar + 56), 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -308,18 +311,19 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
         const uint32_t packed = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
         *reinterpret_cast<uint32_t *>(sWb + layer * L::kWbBytes + tc::unit_offset(c, 0, 2)) = packed;
     }
-    // Streamed weights (C > 128): chunks of KC input channels travel L2 -> shared memory with cp.async into two
-    // buffers, always one chunk ahead of the MMAs; `wn` counts the chunks consumed so far (buffer = wn & 1).
+    // Streamed weights (C > 128): chunks of KC input channels travel L2 -> shared memory as ONE bulk copy each (TMA engine,
+    // cp.async.bulk; the packed chunk is contiguous) into two buffers, always one chunk ahead of the MMAs; only the thread that
+    // issues the MMAs waits for a chunk (mbarrier complete_tx).  `wn` counts the chunks consumed so far: chunk wn lives in
+    // buffer wn & 1 and is that buffer's (wn >> 1)-th use.  (Called by ONE thread.)
     uint32_t wn = 0;
     auto prefetch_wchunk = [&](const uint8_t *src, uint32_t buf) {
-        const uint32_t dst = tc::smem_u32(sW) + buf * L::kWChunkBytes;
-        for (int o = tid * 16; o < L::kWChunkBytes; o += NT * 16) tc::cp_async16(dst + o, src + o);
-        tc::cp_async_commit();
+        tc::mbar_expect_tx(wbar + buf * 8, L::kWChunkBytes);
+        tc::bulk_load_1d(tc::smem_u32(sW) + buf * L::kWChunkBytes, src, L::kWChunkBytes, wbar + buf * 8);
     };
     if (L::kResident) {
         copy_chunk<NT>(sW, p.wimg2, L::kWChunkBytes);
         copy_chunk<NT>(sW + L::kWChunkBytes, p.wimg3, L::kWChunkBytes);
-    } else {
+    } else if (tid == 0) {
         prefetch_wchunk(p.wimg2, 0);
     }
     tc::fence_proxy_async();
@@ -577,25 +581,26 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                     }
                     if (ch == 0 && grp == 0)   // bias flag of the row: bf16 (1, 1) or (0, 0)
                         tc::sts_u32(ab_row, (int32_t)tc::lds_u32(sidx_addr + (uint32_t)(((par * K + k) * kTile + row) * 4)) >= 0 ? 0x3F803F80u : 0u);
-                    if (!L::kResident) tc::cp_async_wait_all();   // this thread's part of the weight chunk has landed
                     tc::fence_proxy_async();
                     tc::fence_before_sync();
                     __syncthreads();
                     if (issuer()) {
+                        if (!L::kResident) tc::mbar_wait_a(wbar + (wn & 1) * 8, (wn >> 1) & 1u);   // this step's weight chunk has landed
                         tc::fence_after_sync();
                         if (ch == 0)
                             tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr, 128, 256), idesc, 0u);
                         issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? 0 : (wn & 1) * L::kWChunkBytes), tmem_acc, true);
                         tc::commit(bar);
+                        if (!L::kResident) {
+                            // next chunk in the tile's fixed sequence: W2 chunks of every round, then the W3 chunks; its buffer was
+                            // last read by the previous chunk step's MMAs, which every thread has seen complete
+                            const uint8_t *nsrc = ch + 1 < L::kChunks ? p.wimg2 + (size_t)(ch + 1) * L::kWChunkBytes
+                                                  : k + 1 < R        ? p.wimg2
+                                                                     : p.wimg3;
+                            prefetch_wchunk(nsrc, (wn + 1) & 1);
+                        }
                     }
-                    if (!L::kResident) {
-                        // next chunk in the tile's fixed sequence: W2 chunks of every round, then the W3 chunks
-                        const uint8_t *nsrc = ch + 1 < L::kChunks ? p.wimg2 + (size_t)(ch + 1) * L::kWChunkBytes
-                                              : k + 1 < R        ? p.wimg2
-                                                                 : p.wimg3;
-                        ++wn;
-                        prefetch_wchunk(nsrc, wn & 1);   // its buffer was last read by the previous chunk's MMAs, already complete
-                    }
+                    if (!L::kResident) ++wn;
                     if (kPipe2) {   // the next chunk step's rows: this round's next chunk, or the first chunk of the next round
                         if (ch + 1 < L::kChunks) gather_chunk(k, ch + 1);
                         else if (k + 1 < R) gather_chunk(k + 1, 0);
@@ -665,23 +670,23 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         const uint32_t nv16 = __float_as_uint((float)n_valid) >> 16;   // small integers are exact in bf16
                         tc::sts_u32(ab_row, nv16 | (nv16 << 16));
                     }
-                    if (!L::kResident) tc::cp_async_wait_all();
                     tc::fence_proxy_async();
                     tc::fence_before_sync();
                     __syncthreads();
                     if (issuer()) {
+                        if (!L::kResident) tc::mbar_wait_a(wbar + (wn & 1) * 8, (wn >> 1) & 1u);
                         tc::fence_after_sync();
                         if (ch == 0)
                             tc::mma_bf16(tmem_acc, tc::make_desc(sAb_addr, 128, 256), tc::make_desc(sWb_addr + L::kWbBytes, 128, 256),
                                          idesc, 0u);
                         issue_chunk<C, NS, KC>(sA_addr, sW_addr + (L::kResident ? L::kWChunkBytes : (wn & 1) * L::kWChunkBytes), tmem_acc, true);
                         tc::commit(bar);
+                        if (!L::kResident) {   // next: the following W3 chunk, or the first W2 chunk for the next tile
+                            const uint8_t *nsrc = ch + 1 < L::kChunks ? p.wimg3 + (size_t)(ch + 1) * L::kWChunkBytes : p.wimg2;
+                            prefetch_wchunk(nsrc, (wn + 1) & 1);
+                        }
                     }
-                    if (!L::kResident) {   // next: the following W3 chunk, or the first W2 chunk for the next tile
-                        const uint8_t *nsrc = ch + 1 < L::kChunks ? p.wimg3 + (size_t)(ch + 1) * L::kWChunkBytes : p.wimg2;
-                        ++wn;
-                        prefetch_wchunk(nsrc, wn & 1);
-                    }
+                    if (!L::kResident) ++wn;
                     tc::mbar_wait(bar, phase);
                     phase ^= 1u;
                     tc::fence_after_sync();
@@ -753,7 +758,8 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
         }
     }
 
-    tc::cp_async_wait_all();   // the weight chunk prefetched for a tile that never came
+    tc::cp_async_wait_all();
+    if (!L::kResident && tid == 0) tc::mbar_wait_a(wbar + (wn & 1) * 8, (wn >> 1) & 1u);   // the weight chunk prefetched for a tile that never came
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_free(tmem_base, L::kTmemCols);

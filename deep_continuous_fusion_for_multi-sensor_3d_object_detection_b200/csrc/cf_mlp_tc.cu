@@ -1357,11 +1357,12 @@ struct Mlp1MultiParams {
 template <int NS>
 __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
 {
-    // warps 0-15: workers (operand build, weight prefetch, epilogues; 4 threads per row split the columns of a chunk);
-    // warp 16: its lane 0 only issues the MMAs, so the ~70 tcgen05.mma of a chunk never sit in front of an epilogue
+    // warps 0-15: workers (operand build, epilogues; 4 threads per row split the columns of a chunk);
+    // warp 16: one elected lane streams the weight chunks (two cp.async.bulk per chunk: TMA engine, mbarrier complete_tx) and
+    // issues the MMAs (descriptors in uniform registers), so the ~70 tcgen05.mma of a chunk never sit in front of an epilogue
     constexpr int NT = kMultiThreads - 32, NW = NT / 32, kIssuer = NT, kColGroups = NT / kTile;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar[2];
+    __shared__ uint64_t bar[2], wbar[2];   // MMAs of a chunk complete; weights of a chunk have landed
     __shared__ uint32_t tmem_slot;
     const int Ci = p.Ci, kc_units = Ci / 8;
     const int a_bytes = NS * kTile * Ci * 2, w_bytes = NS * kTile * Ci * 2;
@@ -1375,6 +1376,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     if (tid == 0) {
         tc::mbar_init(&bar[0], 1);
         tc::mbar_init(&bar[1], 1);
+        tc::mbar_init(&wbar[0], 1);
+        tc::mbar_init(&wbar[1], 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -1396,18 +1399,23 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     const uint32_t sbo = kc_units * 128, lbo = 128;
     uint32_t ph0 = 0, ph1 = 0;
     uint32_t cn = 0;   // chunks issued so far: weight buffer, accumulator and mbarrier of a chunk = cn & 1
-    // the chunk's rows of a packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes); cp.async
+    // the chunk's rows of a packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes): one bulk copy
+    // each, both completing on the buffer's mbarrier.  Called by ONE thread (the elected lane of the issuer warp).
+    const uint32_t wbar_addr = tc::smem_u32(wbar);
     auto prefetch_w = [&](int j, uint32_t buf) {
-        const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], piece = p.chunk_len[j] * Ci * 2;
+        const int s = p.chunk_scale[j], n0 = p.chunk_n0[j];
+        const uint32_t piece = (uint32_t)(p.chunk_len[j] * Ci * 2);
         const uint8_t *src = p.wimg[s] + (size_t)(n0 / 8) * kc_units * 128;
         const uint32_t dst = sW_addr + buf * w_bytes;
-        for (int o = tid * 16; worker && o < piece; o += NT * 16) {
-            tc::cp_async16(dst + o, src + o);
-            if (NS == 2) tc::cp_async16(dst + kTile * Ci * 2 + o, src + (size_t)p.C[s] * Ci * 2 + o);
-        }
-        tc::cp_async_commit();
+        tc::mbar_expect_tx(wbar_addr + buf * 8, NS * piece);
+        tc::bulk_load_1d(dst, src, piece, wbar_addr + buf * 8);
+        if (NS == 2) tc::bulk_load_1d(dst + kTile * Ci * 2, src + (size_t)p.C[s] * Ci * 2, piece, wbar_addr + buf * 8);
     };
-    prefetch_w(0, 0);
+    const bool issuer_warp = warp == kIssuer / 32;
+    if (issuer_warp) {
+        if (tc::elect_one()) prefetch_w(0, 0);
+        __syncwarp();
+    }
 
     const int64_t tiles_total = (int64_t)p.tiles_per_frame * p.B;
     for (int64_t tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
@@ -1480,11 +1488,11 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         };
         for (int j = 0; j < p.n_chunks; ++j) {
             const int len = p.chunk_len[j];
-            tc::cp_async_wait_all();   // this thread's part of the chunk's weights has landed (prefetched one chunk ahead)
             tc::fence_proxy_async();
             tc::fence_before_sync();
             __syncthreads();
-            if (tid == kIssuer) {
+            if (issuer_warp && tc::elect_one()) {
+                tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk's weights have landed (prefetched one chunk ahead)
                 tc::fence_after_sync();
                 const uint32_t idesc = tc::make_idesc_bf16(kTile, len);
                 const uint32_t w0 = sW_addr + (uint32_t)((cn & 1) * w_bytes), acc = tmem_base + (uint32_t)((cn & 1) * kTile);
@@ -1507,7 +1515,10 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
                 if ((cn - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
                 tc::fence_after_sync();
             }
-            prefetch_w(j + 1 < p.n_chunks ? j + 1 : 0, (cn + 1) & 1);   // next chunk (of this tile, or the first one of the next tile)
+            if (issuer_warp) {   // next chunk (of this tile, or the first one of the next tile): its buffer is free now
+                if (tc::elect_one()) prefetch_w(j + 1 < p.n_chunks ? j + 1 : 0, (cn + 1) & 1);
+                __syncwarp();
+            }
             if (j > 0) epilogue(j - 1, (cn - 1) & 1);   // runs under this chunk's MMAs and the weight prefetch
             ++cn;
         }
@@ -1517,7 +1528,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
             epilogue(p.n_chunks - 1, (cn - 1) & 1);
         }
     }
-    tc::cp_async_wait_all();
+    if (tid == kIssuer) tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk prefetched for a tile that never came
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_free(tmem_base, 256);

@@ -1,21 +1,26 @@
-// cf_fusion_seg.cu -- K-4 for the finest scale (C = 32): the fused MLP + K-sum-pool + BEV add on SEGMENT tiles, as a
-// pipeline in which no warp ever waits for a CTA-wide barrier inside a tile and no BEV byte passes through a register.
+// cf_fusion_seg.cu -- EXPERIMENTAL variant of K-4 for the finest scale (C = 32), opt-in with CF_SEG=1 (the product path is
+// k_fusion_tc in cf_mlp_tc.cu, which is faster: 256 us against 356 us out of place at BASELINE configs[1]; the measurements and
+// what they showed are in profiles/README.md).  It is kept, with a full-size parity test (tests/test_gpu_fullsize.py), as the
+// TMA / mbarrier-pipeline formulation of the layer: the fused MLP + K-sum-pool + BEV add on SEGMENT tiles, in which no warp
+// waits for a CTA-wide barrier inside a tile and no BEV byte passes through a register.
 //
 // Unit of work = a SEGMENT: 32 consecutive BEV cells (linear index), i.e. one 128-byte line of every channel plane.
 // k_seg_compact splits the segments of a frame into those with at least one cell that has a neighbour (front of the list)
 // and those without (back).  At BASELINE configs[1] 57 % of the 32-cell segments are entirely empty (90 % of the empty
 // cells), 31 % entirely live, 12 % mixed.  Tile = 4 live segments = 128 rows = UMMA M.
 //
-// Roles (288 threads, two CTAs per SM):
-//   warps 0-7  build operands and run the epilogues.  Warp w owns rows 16 w .. 16 w + 15 in the operand build (lane = row % 8,
+// Roles (256 threads = 8 warps, two CTAs per SM):
+//   every warp builds operands and runs the epilogues: warp w owns rows 16 w .. 16 w + 15 in the operand build (lane = row % 8,
 //              8 channels) and segment w % 4 / channel half w / 4 in the epilogues (TMEM lanes 32 (w % 4) .. +31).
-//   warp 8     the driver: ONE elected thread waits for operand buffers to fill and issues every tcgen05.mma of the CTA
-//              (descriptors stay in uniform registers, the UTCHMMAs go out back to back).
+//   warp 7     is also the driver: after its own part of a slot it probes (mbarrier.test_wait) whether the slot's operand
+//              buffer is complete and then lets ONE elected lane issue the slot's tcgen05.mma (descriptors stay in uniform
+//              registers, the UTCHMMAs go out back to back).  (A ninth, dedicated driver warp was measured first: with 18
+//              warps per SM the register file gives 96 registers per thread and the gather prefetch spilled.)
 // Data flow of a tile:
 //   * the K neighbour slots are built one after the other into a RING of 3 operand buffers (bf16 hi | lo, 16 KB each); a slot
-//     is handed to the driver through an mbarrier (8 arrivals: one per warp), the driver issues its MMAs into the slot's OWN
-//     TMEM accumulator and commits the buffer back (tcgen05.commit -> mbarrier), so builds, MMAs and the gathers of later
-//     slots overlap; the T rows of slot j + 2 are gathered (LDG.256 into registers) before slot j is built.
+//     is handed to the driver through an mbarrier (8 arrivals: one per warp), its MMAs go into the slot's OWN TMEM accumulator
+//     and commit the buffer back (tcgen05.commit -> mbarrier), so builds, MMAs and the gathers of later slots overlap; the T
+//     rows of slot j + 1 are gathered (LDG.256 into registers) before slot j is built.
 //   * after the last slot one commit tells the warps that all accumulators are complete; ONE epilogue reads them, applies the
 //     ReLU and the valid mask and sums them in registers (the pooled sum never round-trips through TMEM), writes the pooled
 //     tile as the layer-3 operand into the next ring buffer, and the driver issues layer 3 into its own accumulator.
@@ -24,9 +29,10 @@
 //     and a TMA store writes it to `out`: no bev value is ever held in a register across a wait.
 //   * empty segments: every warp also owns one 2 KB staging box through which it copies empty segments bev -> out with a
 //     TMA load / TMA store pair, polled (never waited for) twice per tile: the copy stream runs beside the MLP tiles and costs
-//     two instructions of one lane per 2 KB.
+//     two instructions of one lane per 2 KB (+28 us for 57 % of the map, where the thread copies of k_fusion_tc cost +70 us).
 //   * b2 rides on a constant K=16 step (a column of ones); rows without a k-th neighbour are masked in the epilogue (the
-//     slots of a row are sorted, so slot k is valid iff k < n_valid); n_valid * b3 rides on a K=16 step of layer 3.
+//     slots of a row are sorted, so slot k is valid iff k < n_valid); n_valid * b3 rides on a K=16 step of layer 3.  The second
+//     k-unit of all four bias operands is one shared block of zeros reached through the descriptors' leading byte offset.
 // Arithmetic per element is that of k_fusion_tc (same operand split, same products, fp32 accumulation in TMEM); the K-pool
 // additions run in the same order k = 0 .. K-1.
 #include <cuda.h>

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(128) k_knn_patch(const int32_t *__restrict__ b
                                                    const float4 *__restrict__ sorted, int32_t N, BucketGrid g,
                                                    KnnGeom q, int32_t *__restrict__ knn_idx)
 {
+    constexpr bool kCentreOut = K >= 8;   // candidate order of the gather (see below)
     __shared__ float4 cand_all[4][kCandCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -251,26 +252,48 @@ __global__ void __launch_bounds__(128) k_knn_patch(const int32_t *__restrict__ b
         const int32_t ry0 = bucket_coord(pcy - R, g.gy0, g.inv_cell, g.nby), ry1 = bucket_coord(pcy + R, g.gy0, g.inv_cell, g.nby);
         float thr = q.r2;
         int32_t count = 0;
-        for (int32_t x = rx0; x <= rx1; ++x) {
-            const int32_t s = __ldg(bs + x * g.nby + ry0), e = __ldg(bs + x * g.nby + ry1 + 1);
-            for (int32_t base = s; base < e; base += 32) {
-                const int32_t pidx = base + lane;
-                bool keep = false;
-                float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pidx < e) {
-                    pt = __ldg(sp + pidx);
-                    const float ddx = pt.x - pcx, ddy = pt.y - pcy;
-                    keep = ddx * ddx + ddy * ddy <= R2;
+        auto take = [&](int32_t base, int32_t e) {  // 32 sorted points from `base`, kept ones appended to the chunk
+            const int32_t pidx = base + lane;
+            bool keep = false;
+            float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pidx < e) {
+                pt = __ldg(sp + pidx);
+                const float ddx = pt.x - pcx, ddy = pt.y - pcy;
+                keep = ddx * ddx + ddy * ddy <= R2;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) cand[count + __popc(m & ((1u << lane) - 1u))] = pt;
+            count += __popc(m);
+            if (count > kCandCap - 32) {  // uniform: flush the chunk
+                __syncwarp();
+                for (int32_t t = 0; t < count; ++t) knn_test<K>(cand[t], cx, cy, q.r2, thr, best);
+                __syncwarp();
+                count = 0;
+            }
+        };
+        if (kCentreOut) {
+            // Order matters for speed, not for the result (the keys are a total order).  Bucket rows are visited from the
+            // centre outwards and each row from the centre column outwards, so the K-th distance of every lane tightens
+            // early and far candidates fail the pre-filter instead of walking the K-step insertion network (row-major
+            // order feeds every cell a monotonically approaching sequence).  Measured: K = 10 at configs[2] 1.315 ->
+            // 1.22 ms; K = 5 at configs[1] 0.164 -> 0.170 ms (the short network does not pay for the extra row
+            // bookkeeping), hence the switch on K.
+            const int32_t xc = min(max(bucket_coord(pcx, g.gx0, g.inv_cell, g.nbx), rx0), rx1);
+            const int32_t yc = min(max(bucket_coord(pcy, g.gy0, g.inv_cell, g.nby), ry0), ry1);
+            const int32_t span = max(xc - rx0, rx1 - xc);
+            for (int32_t d = 0; d <= span; ++d) {
+                for (int32_t side = 0; side < (d ? 2 : 1); ++side) {
+                    const int32_t x = side ? xc - d : xc + d;
+                    if (x < rx0 || x > rx1) continue;
+                    const int32_t s = __ldg(bs + x * g.nby + ry0), mid = __ldg(bs + x * g.nby + yc), e = __ldg(bs + x * g.nby + ry1 + 1);
+                    for (int32_t base = mid; base < e; base += 32) take(base, e);
+                    for (int32_t top = mid; top > s; top -= 32) take(max(top - 32, s), top);
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) cand[count + __popc(m & ((1u << lane) - 1u))] = pt;
-                count += __popc(m);
-                if (count > kCandCap - 32) {  // uniform: flush the chunk
-                    __syncwarp();
-                    for (int32_t t = 0; t < count; ++t) knn_test<K>(cand[t], cx, cy, q.r2, thr, best);
-                    __syncwarp();
-                    count = 0;
-                }
+            }
+        } else {
+            for (int32_t x = rx0; x <= rx1; ++x) {
+                const int32_t s = __ldg(bs + x * g.nby + ry0), e = __ldg(bs + x * g.nby + ry1 + 1);
+                for (int32_t base = s; base < e; base += 32) take(base, e);
             }
         }
         __syncwarp();

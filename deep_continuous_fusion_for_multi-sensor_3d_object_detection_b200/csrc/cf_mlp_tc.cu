@@ -30,8 +30,10 @@
 // Weights are pre-packed once per call (k_pack_weights) into the shared-memory operand image, chunked along K;
 // up to C = 128 both layers stay resident in shared memory for the life of the CTA, above that chunks of 64 input
 // channels are streamed from L2 per use.
+#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "cf_common.cuh"
 #include "cf_tcgen05.cuh"
@@ -1356,13 +1358,25 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
 // into one of two buffers, one thread issues the K = Ci MMAs into one of two TMEM accumulators, and the epilogue of the
 // previous chunk (rank-3 offset + bias, write T) runs under them.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kMaxScales = 8, kMaxChunks = 16;
+constexpr int kMaxScales = 8, kMaxChunks = 24;
 constexpr int kMultiThreads = 544;   // 16 worker warps + the MMA issuer warp
+constexpr int kStageGroup = kTile * 128;              // one 128-row x 32-column fp32 block (rows of 128 bytes, SWIZZLE_128B)
+// Per split count: output columns per chunk (UMMA N) and whether full tiles are staged for TMA stores.  The staged path pays
+// when the tables leave for DRAM (bf16 mode at configs[2]: 2.5 GB per step); with two splits the operands leave no room
+// for the staging sets, and at configs[1] the tables stay in L2 where the direct stores were measured faster (114 vs 125 us).
+template <int NS>
+struct MultiShape {
+    static constexpr int kChunkW = NS == 2 ? 128 : 64;
+    static constexpr bool kStaged = NS == 1;
+    static constexpr int kStageSet = (kChunkW / 32) * kStageGroup;   // the staged output of one chunk
+    static constexpr int kStageBytes = kStaged ? 2 * kStageSet : 0;
+};
 struct Mlp1MultiParams {
     const float *feat;
     const float *points;
     const int64_t *num_points;
     int32_t B, N, Ci, tiles_per_frame, n_scales, n_chunks;
+    int32_t tma_out;   // 1: full tiles leave through the tensor maps (every T 16-byte aligned)
     const uint8_t *wimg[kMaxScales];
     const float *W1[kMaxScales];
     const float *b1[kMaxScales];
@@ -1370,22 +1384,35 @@ struct Mlp1MultiParams {
     int32_t C[kMaxScales], foff[kMaxScales];   // channels; offset (floats) of the scale's b1|wx|wy|wz table in shared memory
     int32_t chunk_scale[kMaxChunks], chunk_n0[kMaxChunks], chunk_len[kMaxChunks];
 };
+struct Mlp1Maps {
+    CUtensorMap m[kMaxScales];   // T_s as (C_s, N, B) fp32, box 32 x 128 x 1, SWIZZLE_128B
+};
 
+// K-4a for several scales, one 128-point tile at a time.  Per chunk of <= 64 output columns: the packed weight rows stream
+// L2 -> shared memory (TMA, one chunk ahead) into one of two buffers, one elected lane issues the K = Ci MMAs into one of two
+// TMEM accumulators, and the epilogue of the previous chunk runs under them.  The epilogue of a FULL tile adds the rank-3
+// offset and the bias and stages its 128 x 64 block in shared memory (rows of 128 bytes, 128-byte swizzle: conflict-free
+// STS.128), and one thread hands the block to the TMA engine (cp.async.bulk.tensor.3d store): the table leaves the SM as full
+// lines without passing the LSU again.  (A thread owns one ROW of the accumulator, so direct global stores touch 32 lines per
+// instruction; that made the kernel LSU-bound at a third of the HBM write rate.)  The last, partial tile of a frame stores
+// directly so that rows past num_points stay untouched.
 template <int NS>
-__global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp1MultiParams p)
+__global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp1MultiParams p, const __grid_constant__ Mlp1Maps maps)
 {
     // warps 0-15: workers (operand build, epilogues; 4 threads per row split the columns of a chunk);
     // warp 16: one elected lane streams the weight chunks (two cp.async.bulk per chunk: TMA engine, mbarrier complete_tx) and
-    // issues the MMAs (descriptors in uniform registers), so the ~70 tcgen05.mma of a chunk never sit in front of an epilogue
+    // issues the MMAs (descriptors in uniform registers), so the tcgen05.mma of a chunk never sit in front of an epilogue
     constexpr int NT = kMultiThreads - 32, NW = NT / 32, kIssuer = NT, kColGroups = NT / kTile;
+    constexpr int kChunkW = MultiShape<NS>::kChunkW, kStageSet = MultiShape<NS>::kStageSet, kStageBytes = MultiShape<NS>::kStageBytes;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar[2], wbar[2];   // MMAs of a chunk complete; weights of a chunk have landed
     __shared__ uint32_t tmem_slot;
     const int Ci = p.Ci, kc_units = Ci / 8;
-    const int a_bytes = NS * kTile * Ci * 2, w_bytes = NS * kTile * Ci * 2;
-    uint8_t *sA = smem;
-    uint8_t *sWb = smem + a_bytes;                        // two buffers of w_bytes
-    float *sF = reinterpret_cast<float *>(smem + a_bytes + 2 * w_bytes);
+    const int a_bytes = NS * kTile * Ci * 2, w_bytes = NS * kChunkW * Ci * 2;
+    uint8_t *sStage = smem;                               // two sets of kStageSet bytes (1024-byte aligned)
+    uint8_t *sA = smem + kStageBytes;
+    uint8_t *sWb = sA + a_bytes;                          // two buffers of w_bytes
+    float *sF = reinterpret_cast<float *>(sWb + 2 * w_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), half = tid / kTile;
     const bool worker = tid < NT;
@@ -1398,7 +1425,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         tc::mbar_fence_init();
     }
     __syncwarp();
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 2 * kChunkW);
     for (int s = 0; s < p.n_scales; ++s) {
         const int C = p.C[s];
         float4 *f = reinterpret_cast<float4 *>(sF + p.foff[s]);   // per output channel: (b1, wx, wy, wz)
@@ -1412,10 +1439,14 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sWb);
+    const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sWb), stage_addr = tc::smem_u32(sStage);
     const uint32_t sbo = kc_units * 128, lbo = 128;
     uint32_t ph0 = 0, ph1 = 0;
     uint32_t cn = 0;   // chunks issued so far: weight buffer, accumulator and mbarrier of a chunk = cn & 1
+    uint32_t en = 0;   // staged epilogues so far: staging set of the next one = en & 1
+    int pend_j = -1, pend_b = 0;   // the staged chunk whose stores have not been handed to the TMA engine yet (uniform)
+    int32_t pend_m0 = 0;
+    uint32_t pend_set = 0;
     // the chunk's rows of a packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes): one bulk copy
     // each, both completing on the buffer's mbarrier.  Called by ONE thread (the elected lane of the issuer warp).
     const uint32_t wbar_addr = tc::smem_u32(wbar);
@@ -1426,7 +1457,19 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         const uint32_t dst = sW_addr + buf * w_bytes;
         tc::mbar_expect_tx(wbar_addr + buf * 8, NS * piece);
         tc::bulk_load_1d(dst, src, piece, wbar_addr + buf * 8);
-        if (NS == 2) tc::bulk_load_1d(dst + kTile * Ci * 2, src + (size_t)p.C[s] * Ci * 2, piece, wbar_addr + buf * 8);
+        if (NS == 2) tc::bulk_load_1d(dst + kChunkW * Ci * 2, src + (size_t)p.C[s] * Ci * 2, piece, wbar_addr + buf * 8);
+    };
+    // Called by every thread right after a __syncthreads that follows the staging writes (and their fence.proxy.async):
+    // thread 0 hands the staged block to the TMA engine.  Thread 0 also waits, BEFORE every such barrier, until the engine
+    // has read the blocks it was given earlier, so the set written next (the one of two epilogues ago) is free.
+    auto flush_pending = [&]() {
+        if (pend_j >= 0 && tid == 0) {
+            const int s = p.chunk_scale[pend_j], n0 = p.chunk_n0[pend_j], len = p.chunk_len[pend_j];
+            for (int g = 0; g < len / 32; ++g)
+                tc::tma_store_3d(&maps.m[s], n0 + g * 32, pend_m0, pend_b, stage_addr + pend_set * kStageSet + g * kStageGroup);
+            tc::bulk_commit();
+        }
+        pend_j = -1;
     };
     const bool issuer_warp = warp == kIssuer / 32;
     if (issuer_warp) {
@@ -1440,6 +1483,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
         const int32_t n_pts = valid_points(p.num_points, b, p.N);
         if (m0 >= n_pts) continue;  // uniform across the CTA
+        const bool full = MultiShape<NS>::kStaged && p.tma_out && m0 + kTile <= n_pts;
         // ---- A tile, once for all scales (same lane mapping as k_point_mlp1_tc).  The feature rows stream from DRAM:
         // the loads of a batch of items are all issued before the first one is split and stored ------------------------
         const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
@@ -1482,73 +1526,91 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         auto epilogue = [&](int j, uint32_t buf) {
             const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], len = p.chunk_len[j], C = p.C[s];
             const float4 *f = reinterpret_cast<const float4 *>(sF + p.foff[s]);
-            const uint32_t acc = tmem_base + buf * kTile + lane_off;
+            const uint32_t acc = tmem_base + buf * kChunkW + lane_off;
             float *trow = p.T[s] + ((size_t)b * p.N + m) * C + n0;
+            uint8_t *srow = sStage + (en & 1u) * kStageSet + row * 128;
 #pragma unroll 1
             for (int c = half * 16; worker && c < len; c += 16 * kColGroups) {
                 float z[16];
                 tc::tmem_ld16(acc + c, z);
-                if (live) {
+                if (full || live) {
 #pragma unroll
-                    for (int q8 = 0; q8 < 2; ++q8) {   // 256-bit stores: every lane writes full 32-byte sectors of its row
+                    for (int q8 = 0; q8 < 2; ++q8) {
                         float o[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 w = f[n0 + c + q8 * 8 + i];
                             o[i] = z[q8 * 8 + i] + (w.y * px + w.z * py + w.w * pz) + w.x;
                         }
-                        tc::stg_f32x8(trow + c + q8 * 8, o);
+                        if (full) {   // 16-byte chunk q of the row's 128-byte line sits at q ^ (row & 7)
+                            uint8_t *grp = srow + (c >> 5) * kStageGroup;
+                            const int q = ((c & 31) >> 2) + q8 * 2;
+                            *reinterpret_cast<float4 *>(grp + (((q) ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4 *>(grp + (((q + 1) ^ (row & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
+                        } else {
+                            tc::stg_f32x8(trow + c + q8 * 8, o);   // 256-bit stores: every lane writes full 32-byte sectors of its row
+                        }
                     }
                 }
+            }
+            if (full) {
+                pend_j = j; pend_b = b; pend_m0 = m0; pend_set = en & 1u;
+                ++en;
             }
             tc::fence_before_sync();
         };
-        for (int j = 0; j < p.n_chunks; ++j) {
-            const int len = p.chunk_len[j];
+        // iteration j issues the MMAs of chunk j and runs the epilogue of chunk j - 1 (the last iteration only the epilogue)
+        for (int j = 0; j <= p.n_chunks; ++j) {
             tc::fence_proxy_async();
             tc::fence_before_sync();
+            if (tid == 0) tc::bulk_wait_read0();
             __syncthreads();
-            if (issuer_warp && tc::elect_one()) {
-                tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk's weights have landed (prefetched one chunk ahead)
-                tc::fence_after_sync();
-                const uint32_t idesc = tc::make_idesc_bf16(kTile, len);
-                const uint32_t w0 = sW_addr + (uint32_t)((cn & 1) * w_bytes), acc = tmem_base + (uint32_t)((cn & 1) * kTile);
-                uint32_t accum = 0;
-                for (int kk = 0; kk < Ci / 16; ++kk) {
-                    const uint32_t koff = kk * 2 * lbo;
-                    const uint64_t a_hi = tc::make_desc(sA_addr + koff, lbo, sbo), w_hi = tc::make_desc(w0 + koff, lbo, sbo);
-                    tc::mma_bf16(acc, a_hi, w_hi, idesc, accum);
-                    accum = 1;
-                    if (NS == 2) {
-                        const uint64_t a_lo = tc::make_desc(sA_addr + kTile * Ci * 2 + koff, lbo, sbo);
-                        const uint64_t w_lo = tc::make_desc(w0 + kTile * Ci * 2 + koff, lbo, sbo);
-                        tc::mma_bf16(acc, a_hi, w_lo, idesc, 1);
-                        tc::mma_bf16(acc, a_lo, w_hi, idesc, 1);
+            flush_pending();
+            if (j < p.n_chunks) {
+                if (issuer_warp && tc::elect_one()) {
+                    tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk's weights have landed (prefetched one chunk ahead)
+                    tc::fence_after_sync();
+                    const uint32_t idesc = tc::make_idesc_bf16(kTile, p.chunk_len[j]);
+                    const uint32_t w0 = sW_addr + (uint32_t)((cn & 1) * w_bytes), acc = tmem_base + (uint32_t)((cn & 1) * kChunkW);
+                    uint32_t accum = 0;
+                    for (int kk = 0; kk < Ci / 16; ++kk) {
+                        const uint32_t koff = kk * 2 * lbo;
+                        const uint64_t a_hi = tc::make_desc(sA_addr + koff, lbo, sbo), w_hi = tc::make_desc(w0 + koff, lbo, sbo);
+                        tc::mma_bf16(acc, a_hi, w_hi, idesc, accum);
+                        accum = 1;
+                        if (NS == 2) {
+                            const uint64_t a_lo = tc::make_desc(sA_addr + kTile * Ci * 2 + koff, lbo, sbo);
+                            const uint64_t w_lo = tc::make_desc(w0 + kChunkW * Ci * 2 + koff, lbo, sbo);
+                            tc::mma_bf16(acc, a_hi, w_lo, idesc, 1);
+                            tc::mma_bf16(acc, a_lo, w_hi, idesc, 1);
+                        }
                     }
+                    tc::commit(&bar[cn & 1]);
                 }
-                tc::commit(&bar[cn & 1]);
+                ++cn;
             }
             if (j > 0) {   // the previous chunk's MMAs: once they are complete their weight buffer is free again
-                if ((cn - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+                const uint32_t pb = (cn - (j < p.n_chunks ? 2u : 1u)) & 1u;
+                if (pb) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
                 tc::fence_after_sync();
-            }
-            if (issuer_warp) {   // next chunk (of this tile, or the first one of the next tile): its buffer is free now
-                if (tc::elect_one()) prefetch_w(j + 1 < p.n_chunks ? j + 1 : 0, (cn + 1) & 1);
+                if (j < p.n_chunks && issuer_warp) {   // next chunk (of this tile, or the first one of the next tile): its buffer is free now
+                    if (tc::elect_one()) prefetch_w(j + 1 < p.n_chunks ? j + 1 : 0, pb);
+                    __syncwarp();
+                }
+                epilogue(j - 1, pb);   // runs under this chunk's MMAs and the weight prefetch
+            } else if (issuer_warp) {
+                if (tc::elect_one()) prefetch_w(1 < p.n_chunks ? 1 : 0, cn & 1);   // buffer of the chunk after chunk 0: free since the last tile
                 __syncwarp();
             }
-            if (j > 0) epilogue(j - 1, (cn - 1) & 1);   // runs under this chunk's MMAs and the weight prefetch
-            ++cn;
-        }
-        {
-            if ((cn - 1) & 1) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
-            tc::fence_after_sync();
-            epilogue(p.n_chunks - 1, (cn - 1) & 1);
         }
     }
     if (tid == kIssuer) tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk prefetched for a tile that never came
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_free(tmem_base, 256);
+    flush_pending();
+    if (tid == 0) tc::bulk_wait0();   // the staged blocks have been written before the shared memory goes away
+    if (warp == 0) tc::tmem_free(tmem_base, 2 * kChunkW);
 }
 
 template <int C, int NS>
@@ -1857,6 +1919,31 @@ int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_n
     return launch_status("cf_point_mlp1 (tcgen05)");
 }
 
+// 3-D tensor map over a table T (B, N, C) fp32: x = channel (fastest), y = point, z = frame; box 32 x 128 x 1 with the
+// 128-byte swizzle (the layout the epilogue stages).  Rows past N are clipped by the TMA engine.
+static int make_table_map(CUtensorMap *tm, float *base, int32_t C, int32_t N, int32_t B)
+{
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CF_TRY(cuda_status(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q), "cuTensorMapEncodeTiled entry point"));
+        CF_REQUIRE(f != nullptr && q == cudaDriverEntryPointSuccess, CF_ERR_LAUNCH, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (EncodeTiledFn)f;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)kTile, 1};
+    const cuuint32_t el[3] = {1, 1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_LAUNCH, "cuTensorMapEncodeTiled failed for a (%d, %d, %d) table (%d)", B, N, C, (int)r);
+    return CF_OK;
+}
+
 // returns CF_ERR_UNSUPPORTED (without setting an error) when the shapes do not fit the multi-scale kernel
 int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_t *d_num_points, int32_t B, int32_t N,
                         int32_t Ci, int32_t n_scales, const int32_t *h_C, const float *const *h_W1,
@@ -1868,6 +1955,8 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     Mlp1MultiParams p;
     p.feat = d_feat; p.points = d_points; p.num_points = d_num_points;
     p.B = B; p.N = N; p.Ci = Ci; p.tiles_per_frame = (N + kTile - 1) / kTile; p.n_scales = n_scales;
+    const int chunk_w = NS == 2 ? MultiShape<2>::kChunkW : MultiShape<1>::kChunkW;
+    const int stage_bytes = NS == 2 ? MultiShape<2>::kStageBytes : MultiShape<1>::kStageBytes;
     int chunks = 0, foff = 0;
     for (int s = 0; s < n_scales; ++s) {
         const int C = h_C[s];
@@ -1875,15 +1964,21 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
         p.wimg[s] = (const uint8_t *)h_packed[s]; p.W1[s] = h_W1[s]; p.b1[s] = h_b1[s]; p.T[s] = h_T[s];
         p.C[s] = C; p.foff[s] = foff;
         foff += 4 * C;
-        for (int n0 = 0; n0 < C; n0 += kTile) {
+        for (int n0 = 0; n0 < C; n0 += chunk_w) {
             if (chunks == kMaxChunks) return CF_ERR_UNSUPPORTED;
-            p.chunk_scale[chunks] = s; p.chunk_n0[chunks] = n0; p.chunk_len[chunks] = std::min(kTile, C - n0);
+            p.chunk_scale[chunks] = s; p.chunk_n0[chunks] = n0; p.chunk_len[chunks] = std::min(chunk_w, C - n0);
             ++chunks;
         }
     }
     p.n_chunks = chunks;
-    const size_t smem = (size_t)3 * NS * kTile * Ci * 2 + (size_t)foff * 4;
+    const size_t smem = (size_t)stage_bytes + (size_t)NS * (kTile + 2 * chunk_w) * Ci * 2 + (size_t)foff * 4;
     if (smem > 225 * 1024) return CF_ERR_UNSUPPORTED;
+    Mlp1Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    p.tma_out = stage_bytes > 0;
+    for (int s = 0; s < n_scales; ++s)
+        if (((uintptr_t)h_T[s] & 15u) != 0) p.tma_out = 0;
+    for (int s = 0; s < n_scales && p.tma_out; ++s) CF_TRY(make_table_map(&maps.m[s], h_T[s], h_C[s], N, B));
     auto kern = NS == 2 ? k_point_mlp1_multi<2> : k_point_mlp1_multi<1>;
     CF_TRY(cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "k_point_mlp1_multi smem attribute"));
@@ -1891,7 +1986,7 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     // one CTA per SM (shared memory); an even share of tiles per CTA beats leaving a few CTAs with one tile more
     const int64_t waves = ceil_div64(tiles, sm_count());
     const int64_t grid = std::max<int64_t>(1, ceil_div64(tiles, waves));
-    kern<<<(unsigned)grid, kMultiThreads, smem, st>>>(p);
+    kern<<<(unsigned)grid, kMultiThreads, smem, st>>>(p, maps);
     count_launches(1);
     return launch_status("cf_point_mlp1_multi (tcgen05)");
 }

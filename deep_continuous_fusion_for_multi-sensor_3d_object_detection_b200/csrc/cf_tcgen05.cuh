@@ -169,6 +169,11 @@ __device__ __forceinline__ void tma_store_2d(const void *tmap, int32_t x, int32_
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(src) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void *tmap, int32_t x, int32_t y, int32_t z, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(x), "r"(y), "r"(z), "r"(src)
+                 : "memory");
+}
 // 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP): `bytes` a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar_addr)
 {

@@ -252,14 +252,14 @@ class GpuPipeline:
         self.size = (float(wl["config"]["image_width"]), float(wl["config"]["image_height"]))
         self.live_frac, self.valid_rows = {}, {}
 
-    def step(self, bev=None, points=None, counts=None, img=None):
+    def step(self, bev=None, points=None, counts=None, img=None, inplace=False):
         torch = self.torch
         bev = self.bev if bev is None else bev
         with torch.no_grad():
             frames = self.dcf.FrameContext(self.points if points is None else points,
                                            self.counts if counts is None else counts, self.grid)
             frames.gather(self.img if img is None else img, calib=self.calib, img_size=self.size)
-            return self.dcf.fuse_scales(frames, self.layers, bev)
+            return self.dcf.fuse_scales(frames, self.layers, bev, inplace=inplace)
 
     def timed_ops(self):
         """One step with a CUDA-event pair around every C-ABI call -> {op name: ms}, per-launch list."""
@@ -381,6 +381,31 @@ def run_gpu(args):
     barrier()
     ms_steady = g0.elapsed_time(g1)
 
+    # ---- the same step writing into its input maps (cf_fusion_fwd with d_out == d_bev) -----------------
+    # How the drop-in model (inference) and the end-to-end runner below call the layer: cells without a LiDAR point in
+    # reach then cost no memory traffic.  The headline `value` above stays out of place (the reference allocates a new map,
+    # model.py:74-78).  Every replay adds the fused term to the same maps again; the kernels' work does not depend on the
+    # map values, and 3 + K additions of O(1) terms stay far from overflow.
+    ms_inplace = None
+    if graph is not None:
+        bev_io = [b.clone() for b in pipe.bev]
+        for _ in range(2):
+            pipe.step(bev=bev_io, inplace=True)
+        torch.cuda.synchronize()
+        graph_ip = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_ip):
+            pipe.step(bev=bev_io, inplace=True)
+        graph_ip.replay()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        i0.record()
+        for _ in range(args.steps):
+            graph_ip.replay()
+        i1.record()
+        barrier()
+        ms_inplace = i0.elapsed_time(i1)
+        del graph_ip, bev_io
+
     # ---- end to end: host buffers in, host buffers out ------------------------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_points, h_counts, h_img = pin(wl["points"]), pin(wl["num_points"]), pin(wl["img_feat"])
@@ -465,7 +490,8 @@ def run_gpu(args):
     barrier()
 
     # ---- max over ranks ---------------------------------------------------------------------------------
-    ms, ms_e2e, ms_steady, inv_h2d, inv_d2h = dcf.dist_util.max_over_ranks([ms, ms_e2e, ms_steady, 1.0 / h2d_gbs, 1.0 / d2h_gbs], device=device)
+    ms, ms_e2e, ms_steady, inv_h2d, inv_d2h, ms_inplace = dcf.dist_util.max_over_ranks(
+        [ms, ms_e2e, ms_steady, 1.0 / h2d_gbs, 1.0 / d2h_gbs, ms_inplace if ms_inplace is not None else -1.0], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -588,6 +614,10 @@ def run_gpu(args):
         "config": {"workload": workload_label(args.workload, wl)},
         "run": {"mlp_mode": mode, "frames_per_step_per_gpu": B, "launch": "eager" if graph is None else "cuda_graph_replay",
                 "l2_policy": f"inputs_exceed_l2 (BEV in+out {2 * sum(b.numel() * 4 for b in pipe.bev) / 1e6:.0f} MB per step vs 126 MB L2)"},
+        "in_place": None if ms_inplace < 0 else {
+            "ms_per_step": round(ms_inplace / args.steps, 4), "value": round(dcf.dist_util.aggregate_rate(B, world, args.steps, ms_inplace), 2),
+            "unit": UNIT, "note": "same step, same protocol, the fused layer writing into its input maps (d_out == d_bev), as the "
+                                  "drop-in model at inference and the e2e runner call it"},
         "steady_200_replays": {"replays": n_steady, "ms_per_step": round(ms_steady / n_steady, 4),
                                "value": round(dcf.dist_util.aggregate_rate(B, world, n_steady, ms_steady), 2), "unit": UNIT},
         "e2e": {"value": round(dcf.dist_util.aggregate_rate(B, world, e2e_steps, ms_e2e), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -1367,9 +1367,13 @@ constexpr int kStageGroup = kTile * 128;              // one 128-row x 32-column
 template <int NS>
 struct MultiShape {
     static constexpr int kChunkW = NS == 2 ? 128 : 64;
+    static constexpr int kWBufs = 2;       // weight ring: a chunk is requested kWBufs chunks before its MMAs
+                                           // (4 buffers and 3 staging sets measured the same 0.99 ms at configs[2]: the kernel is
+                                           // bound by the DRAM write rate, 2.5 GB of tables at ~2.5 TB/s + 0.5 GB of reads)
     static constexpr bool kStaged = NS == 1;
     static constexpr int kStageSet = (kChunkW / 32) * kStageGroup;   // the staged output of one chunk
-    static constexpr int kStageBytes = kStaged ? 2 * kStageSet : 0;
+    static constexpr int kStageSets = 2;   // a staged block has kStageSets - 1 chunk iterations to be read by the TMA engine
+    static constexpr int kStageBytes = kStaged ? kStageSets * kStageSet : 0;
 };
 struct Mlp1MultiParams {
     const float *feat;
@@ -1404,15 +1408,16 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     // issues the MMAs (descriptors in uniform registers), so the tcgen05.mma of a chunk never sit in front of an epilogue
     constexpr int NT = kMultiThreads - 32, NW = NT / 32, kIssuer = NT, kColGroups = NT / kTile;
     constexpr int kChunkW = MultiShape<NS>::kChunkW, kStageSet = MultiShape<NS>::kStageSet, kStageBytes = MultiShape<NS>::kStageBytes;
+    constexpr uint32_t kWBufs = MultiShape<NS>::kWBufs, kStageSets = MultiShape<NS>::kStageSets;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar[2], wbar[2];   // MMAs of a chunk complete; weights of a chunk have landed
+    __shared__ uint64_t bar[2], wbar[kWBufs];   // MMAs of a chunk complete; weights of a chunk have landed
     __shared__ uint32_t tmem_slot;
     const int Ci = p.Ci, kc_units = Ci / 8;
     const int a_bytes = NS * kTile * Ci * 2, w_bytes = NS * kChunkW * Ci * 2;
     uint8_t *sStage = smem;                               // two sets of kStageSet bytes (1024-byte aligned)
     uint8_t *sA = smem + kStageBytes;
-    uint8_t *sWb = sA + a_bytes;                          // two buffers of w_bytes
-    float *sF = reinterpret_cast<float *>(sWb + 2 * w_bytes);
+    uint8_t *sWb = sA + a_bytes;                          // ring of kWBufs buffers of w_bytes
+    float *sF = reinterpret_cast<float *>(sWb + kWBufs * w_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), half = tid / kTile;
     const bool worker = tid < NT;
@@ -1420,8 +1425,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     if (tid == 0) {
         tc::mbar_init(&bar[0], 1);
         tc::mbar_init(&bar[1], 1);
-        tc::mbar_init(&wbar[0], 1);
-        tc::mbar_init(&wbar[1], 1);
+        for (uint32_t i = 0; i < kWBufs; ++i) tc::mbar_init(&wbar[i], 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -1442,15 +1446,17 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sWb), stage_addr = tc::smem_u32(sStage);
     const uint32_t sbo = kc_units * 128, lbo = 128;
     uint32_t ph0 = 0, ph1 = 0;
-    uint32_t cn = 0;   // chunks issued so far: weight buffer, accumulator and mbarrier of a chunk = cn & 1
-    uint32_t en = 0;   // staged epilogues so far: staging set of the next one = en & 1
+    uint32_t cn = 0;   // chunks issued so far: accumulator and MMA mbarrier of a chunk = cn & 1, weight buffer = cn % kWBufs
+    uint32_t en = 0;   // staging set of the next staged epilogue (they rotate)
     int pend_j = -1, pend_b = 0;   // the staged chunk whose stores have not been handed to the TMA engine yet (uniform)
     int32_t pend_m0 = 0;
     uint32_t pend_set = 0;
     // the chunk's rows of a packed image: hi rows, then lo rows (each a contiguous run of len * Ci * 2 bytes): one bulk copy
     // each, both completing on the buffer's mbarrier.  Called by ONE thread (the elected lane of the issuer warp).
     const uint32_t wbar_addr = tc::smem_u32(wbar);
-    auto prefetch_w = [&](int j, uint32_t buf) {
+    auto prefetch_w = [&](uint32_t g) {   // g = running chunk number: chunk g % n_chunks of some tile, buffer g % kWBufs
+        const int j = (int)(g % (uint32_t)p.n_chunks);
+        const uint32_t buf = g % kWBufs;
         const int s = p.chunk_scale[j], n0 = p.chunk_n0[j];
         const uint32_t piece = (uint32_t)(p.chunk_len[j] * Ci * 2);
         const uint8_t *src = p.wimg[s] + (size_t)(n0 / 8) * kc_units * 128;
@@ -1461,7 +1467,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     };
     // Called by every thread right after a __syncthreads that follows the staging writes (and their fence.proxy.async):
     // thread 0 hands the staged block to the TMA engine.  Thread 0 also waits, BEFORE every such barrier, until the engine
-    // has read the blocks it was given earlier, so the set written next (the one of two epilogues ago) is free.
+    // has read all but its latest kStageSets - 2 blocks, so the set written next (used kStageSets epilogues ago) is free.
     auto flush_pending = [&]() {
         if (pend_j >= 0 && tid == 0) {
             const int s = p.chunk_scale[pend_j], n0 = p.chunk_n0[pend_j], len = p.chunk_len[pend_j];
@@ -1473,7 +1479,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     };
     const bool issuer_warp = warp == kIssuer / 32;
     if (issuer_warp) {
-        if (tc::elect_one()) prefetch_w(0, 0);
+        if (tc::elect_one())
+            for (uint32_t g = 0; g < kWBufs; ++g) prefetch_w(g);
         __syncwarp();
     }
 
@@ -1528,7 +1535,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
             const float4 *f = reinterpret_cast<const float4 *>(sF + p.foff[s]);
             const uint32_t acc = tmem_base + buf * kChunkW + lane_off;
             float *trow = p.T[s] + ((size_t)b * p.N + m) * C + n0;
-            uint8_t *srow = sStage + (en & 1u) * kStageSet + row * 128;
+            uint8_t *srow = sStage + en * kStageSet + row * 128;
 #pragma unroll 1
             for (int c = half * 16; worker && c < len; c += 16 * kColGroups) {
                 float z[16];
@@ -1554,8 +1561,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
                 }
             }
             if (full) {
-                pend_j = j; pend_b = b; pend_m0 = m0; pend_set = en & 1u;
-                ++en;
+                pend_j = j; pend_b = b; pend_m0 = m0; pend_set = en;
+                en = en + 1 == kStageSets ? 0 : en + 1;
             }
             tc::fence_before_sync();
         };
@@ -1563,15 +1570,15 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         for (int j = 0; j <= p.n_chunks; ++j) {
             tc::fence_proxy_async();
             tc::fence_before_sync();
-            if (tid == 0) tc::bulk_wait_read0();
+            if (tid == 0) tc::bulk_wait_read<kStageSets - 2>();   // all but the latest kStageSets - 2 blocks have been read
             __syncthreads();
             flush_pending();
             if (j < p.n_chunks) {
                 if (issuer_warp && tc::elect_one()) {
-                    tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk's weights have landed (prefetched one chunk ahead)
+                    tc::mbar_wait_a(wbar_addr + (cn % kWBufs) * 8, (cn / kWBufs) & 1u);   // the chunk's weights have landed (requested kWBufs chunks ago)
                     tc::fence_after_sync();
                     const uint32_t idesc = tc::make_idesc_bf16(kTile, p.chunk_len[j]);
-                    const uint32_t w0 = sW_addr + (uint32_t)((cn & 1) * w_bytes), acc = tmem_base + (uint32_t)((cn & 1) * kChunkW);
+                    const uint32_t w0 = sW_addr + (uint32_t)((cn % kWBufs) * w_bytes), acc = tmem_base + (uint32_t)((cn & 1) * kChunkW);
                     uint32_t accum = 0;
                     for (int kk = 0; kk < Ci / 16; ++kk) {
                         const uint32_t koff = kk * 2 * lbo;
@@ -1593,18 +1600,17 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
                 const uint32_t pb = (cn - (j < p.n_chunks ? 2u : 1u)) & 1u;
                 if (pb) { tc::mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { tc::mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
                 tc::fence_after_sync();
-                if (j < p.n_chunks && issuer_warp) {   // next chunk (of this tile, or the first one of the next tile): its buffer is free now
-                    if (tc::elect_one()) prefetch_w(j + 1 < p.n_chunks ? j + 1 : 0, pb);
+                if (issuer_warp) {   // the weight buffer of the chunk just completed is free: request the chunk that uses it next
+                    const uint32_t done = cn - (j < p.n_chunks ? 2u : 1u);
+                    if (tc::elect_one()) prefetch_w(done + kWBufs);
                     __syncwarp();
                 }
                 epilogue(j - 1, pb);   // runs under this chunk's MMAs and the weight prefetch
-            } else if (issuer_warp) {
-                if (tc::elect_one()) prefetch_w(1 < p.n_chunks ? 1 : 0, cn & 1);   // buffer of the chunk after chunk 0: free since the last tile
-                __syncwarp();
             }
         }
     }
-    if (tid == kIssuer) tc::mbar_wait_a(wbar_addr + (cn & 1) * 8, (cn >> 1) & 1u);   // the chunk prefetched for a tile that never came
+    if (tid == kIssuer)   // the chunks requested for tiles that never came
+        for (uint32_t g = cn; g < cn + kWBufs; ++g) tc::mbar_wait_a(wbar_addr + (g % kWBufs) * 8, (g / kWBufs) & 1u);
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -1971,7 +1977,8 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
         }
     }
     p.n_chunks = chunks;
-    const size_t smem = (size_t)stage_bytes + (size_t)NS * (kTile + 2 * chunk_w) * Ci * 2 + (size_t)foff * 4;
+    const int w_bufs = NS == 2 ? MultiShape<2>::kWBufs : MultiShape<1>::kWBufs;
+    const size_t smem = (size_t)stage_bytes + (size_t)NS * (kTile + w_bufs * chunk_w) * Ci * 2 + (size_t)foff * 4;
     if (smem > 225 * 1024) return CF_ERR_UNSUPPORTED;
     Mlp1Maps maps;
     memset(&maps, 0, sizeof(maps));

@@ -679,6 +679,28 @@ def side_workload(dcf, name, device, peak, replays=60):
            "replays": replays, "layer_frac_of_hbm_peak": round(layer_bytes * B / (ms * 1e-3) / 1e9 / peak, 4), "kernel_ms": per_op}
     del graph, pipe
     torch.cuda.empty_cache()
+    if mode == "bf16":
+        # the same workload with the layer-1 tables stored as bf16 too (CF_MODE_BF16_TABLES, inference only; same 1e-2 tolerance,
+        # tests/test_gpu_fullsize.py): half the table bytes written by K-4a and gathered by K-4
+        pipe = GpuPipeline(dcf, wl, "bf16t", device)
+        for _ in range(3):
+            pipe.step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            pipe.step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(replays):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms_t = a.elapsed_time(b) / replays
+        out["bf16_tables"] = {"mlp_mode": "bf16t", "value": round(B / (ms_t * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms_t, 4), "replays": replays}
+        del graph, pipe
+        torch.cuda.empty_cache()
     return out
 
 
@@ -794,7 +816,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg1")
-    ap.add_argument("--mode", default=None, help="fp32 | bf16 | simt (default: the workload's)")
+    ap.add_argument("--mode", default=None, help="fp32 | bf16 | bf16t (bf16 with bf16 tables) | simt (default: the workload's)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the side records (cfg2 sub-record, model end to end)")

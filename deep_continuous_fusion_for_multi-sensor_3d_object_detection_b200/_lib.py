@@ -10,8 +10,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_PKG, "libcf_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
-MODE_FP32, MODE_BF16, MODE_SIMT = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "simt": MODE_SIMT}
+MODE_FP32, MODE_BF16, MODE_SIMT, MODE_BF16_TABLES = 0, 1, 2, 3
+# "bf16t" = CF_MODE_BF16_TABLES: bf16 operands AND bf16 layer-1 tables (inference only)
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "simt": MODE_SIMT, "bf16t": MODE_BF16_TABLES}
 MAX_K = 16
 ABI_VERSION = 2
 

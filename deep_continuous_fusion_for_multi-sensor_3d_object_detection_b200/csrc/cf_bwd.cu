@@ -495,6 +495,7 @@ extern "C" int cf_fusion_bwd(const float *d_gout, const float *d_feat, const flo
                CF_ERR_ARG, "cf_fusion_bwd: null pointer");
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && C > 0 && H > 0 && W > 0 && K >= 1 && K <= CF_MAX_K && Ci > 0 && Ci % 4 == 0,
                CF_ERR_ARG, "cf_fusion_bwd: bad extents");
+    CF_REQUIRE(mode != CF_MODE_BF16_TABLES, CF_ERR_UNSUPPORTED, "cf_fusion_bwd: CF_MODE_BF16_TABLES is an inference mode (the backward reads fp32 tables)");
     CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_FP32_SIMT, CF_ERR_ARG, "cf_fusion_bwd: unknown mode %d",
                mode);
     CF_REQUIRE(aligned16(d_workspace), CF_ERR_ALIGN, "cf_fusion_bwd: workspace must be 16-byte aligned");

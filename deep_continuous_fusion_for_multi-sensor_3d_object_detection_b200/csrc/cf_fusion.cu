@@ -29,7 +29,8 @@ extern "C" int cf_fusion_pack_weights(const float *d_W2, const float *d_W3, int3
     using namespace cf;
     CF_TRY(require_sm100());
     CF_REQUIRE(d_W2 && d_W3 && d_packed, CF_ERR_ARG, "cf_fusion_pack_weights: null pointer");
-    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_fusion_pack_weights: mode %d has no packed form", mode);
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_BF16_TABLES, CF_ERR_ARG,
+               "cf_fusion_pack_weights: mode %d has no packed form", mode);
     CF_REQUIRE(aligned16(d_packed), CF_ERR_ALIGN, "cf_fusion_pack_weights: buffer must be 16-byte aligned");
     return fusion_tc_pack(d_W2, d_W3, C, mode, d_packed, (cudaStream_t)stream);
 }
@@ -63,6 +64,7 @@ extern "C" int cf_fusion_fwd(const float *d_bev, const float *d_T, const int32_t
                                d_b3, d_out, d_workspace, st);
         case CF_MODE_FP32:
         case CF_MODE_BF16:
+        case CF_MODE_BF16_TABLES:   // d_T holds bf16 rows
             CF_REQUIRE(d_packed == nullptr || aligned16(d_packed), CF_ERR_ALIGN, "cf_fusion_fwd: packed weights must be 16-byte aligned");
             return fusion_tc(d_bev, d_T, d_knn_idx, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_W2, d_b2, d_W3,
                              d_b3, d_out, mode, d_packed, d_workspace, st);

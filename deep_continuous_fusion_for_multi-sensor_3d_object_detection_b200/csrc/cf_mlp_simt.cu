@@ -246,7 +246,8 @@ extern "C" int cf_point_mlp1_pack_weights(const float *d_W1, int32_t Ci, int32_t
     using namespace cf;
     CF_TRY(require_sm100());
     CF_REQUIRE(d_W1 && d_packed && aligned16(d_packed), CF_ERR_ARG, "cf_point_mlp1_pack_weights: bad pointer");
-    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_point_mlp1_pack_weights: mode %d has no packed form", mode);
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_BF16_TABLES, CF_ERR_ARG,
+               "cf_point_mlp1_pack_weights: mode %d has no packed form", mode);
     return point_mlp1_tc_pack(d_W1, Ci, C, mode, d_packed, (cudaStream_t)stream);
 }
 
@@ -265,9 +266,23 @@ extern "C" int cf_point_mlp1(const float *d_feat, const float *d_points, const i
     CF_REQUIRE(d_feat && d_points && d_num_points && d_W1 && d_b1 && d_T, CF_ERR_ARG, "cf_point_mlp1: null pointer");
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && Ci > 0 && C > 0, CF_ERR_ARG, "cf_point_mlp1: bad extents");
     CF_REQUIRE(Ci % 4 == 0, CF_ERR_ARG, "cf_point_mlp1: Ci=%d must be a multiple of 4", Ci);
-    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_FP32_SIMT, CF_ERR_ARG,
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_FP32_SIMT || mode == CF_MODE_BF16_TABLES, CF_ERR_ARG,
                "cf_point_mlp1: unknown mode %d", mode);
     CF_REQUIRE(aligned16(d_feat) && aligned16(d_T), CF_ERR_ALIGN, "cf_point_mlp1: feat/T must be 16-byte aligned");
+    if (mode == CF_MODE_BF16_TABLES) {   // bf16 rows: the multi-scale kernel with one scale (no FFMA fallback)
+        CF_REQUIRE(d_packed != nullptr || d_workspace != nullptr, CF_ERR_ARG, "cf_point_mlp1: CF_MODE_BF16_TABLES needs packed weights or a workspace");
+        CF_REQUIRE(aligned16(d_workspace) && aligned16(d_packed) && (reinterpret_cast<uintptr_t>(d_feat) & 31u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_T) & 31u) == 0,
+                   CF_ERR_ALIGN, "cf_point_mlp1: CF_MODE_BF16_TABLES needs 32-byte aligned feat / T and 16-byte aligned weights");
+        const void *img = d_packed;
+        if (!img) {
+            CF_TRY(point_mlp1_tc_pack(d_W1, Ci, C, mode, d_workspace, (cudaStream_t)stream));
+            img = d_workspace;
+        }
+        const int rc = point_mlp1_multi_tc(d_feat, d_points, d_num_points, B, N, Ci, 1, &C, &d_W1, &d_b1, &d_T, mode, &img, (cudaStream_t)stream);
+        if (rc == CF_ERR_UNSUPPORTED) set_error("cf_point_mlp1: CF_MODE_BF16_TABLES does not support Ci=%d, C=%d", Ci, C);
+        return rc;
+    }
     if (mode != CF_MODE_FP32_SIMT && (d_workspace != nullptr || d_packed != nullptr)) {
         CF_REQUIRE(aligned16(d_workspace) && aligned16(d_packed), CF_ERR_ALIGN, "cf_point_mlp1: workspace / packed weights must be 16-byte aligned");
         const int rc = point_mlp1_tc(d_feat, d_points, d_num_points, B, N, Ci, C, d_W1, d_b1, d_T, mode, d_packed,
@@ -287,7 +302,8 @@ extern "C" int cf_point_mlp1_multi(const float *d_feat, const float *d_points, c
     CF_REQUIRE(d_feat && d_points && d_num_points && h_C && h_W1 && h_b1 && h_T && h_packed, CF_ERR_ARG,
                "cf_point_mlp1_multi: null pointer");
     CF_REQUIRE(B > 0 && B <= 65535 && N > 0 && Ci > 0 && n_scales > 0, CF_ERR_ARG, "cf_point_mlp1_multi: bad extents");
-    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16, CF_ERR_ARG, "cf_point_mlp1_multi: mode %d has no tensor-core path", mode);
+    CF_REQUIRE(mode == CF_MODE_FP32 || mode == CF_MODE_BF16 || mode == CF_MODE_BF16_TABLES, CF_ERR_ARG,
+               "cf_point_mlp1_multi: mode %d has no tensor-core path", mode);
     CF_REQUIRE((reinterpret_cast<uintptr_t>(d_feat) & 31u) == 0, CF_ERR_ALIGN, "cf_point_mlp1_multi: feat must be 32-byte aligned");
     for (int s = 0; s < n_scales && s < 64; ++s) {
         CF_REQUIRE(h_W1[s] && h_b1[s] && h_T[s] && h_packed[s], CF_ERR_ARG, "cf_point_mlp1_multi: null pointer for scale %d", s);

@@ -127,6 +127,24 @@ constexpr int kCopyBatch = CF_COPY_BATCH;  // channels per copy unit and thread 
 __device__ __align__(32) float g_neg_row[256] = {CF_NEG64, CF_NEG64, CF_NEG64, CF_NEG64};
 #undef CF_NEG64
 #undef CF_NEG8
+// the same row for bf16 tables (CF_MODE_BF16_TABLES): 0xF14A = bf16(-1e30)
+#define CF_NEGH8 0xF14A, 0xF14A, 0xF14A, 0xF14A, 0xF14A, 0xF14A, 0xF14A, 0xF14A
+#define CF_NEGH64 CF_NEGH8, CF_NEGH8, CF_NEGH8, CF_NEGH8, CF_NEGH8, CF_NEGH8, CF_NEGH8, CF_NEGH8
+__device__ __align__(32) uint16_t g_neg_row_h[256] = {CF_NEGH64, CF_NEGH64, CF_NEGH64, CF_NEGH64};
+#undef CF_NEGH64
+#undef CF_NEGH8
+
+// element type of the layer-1 tables a fused kernel gathers from, and its all-(-1e30) row
+template <bool TH>
+struct TableT {
+    using type = float;
+    static __device__ __forceinline__ const float *neg() { return g_neg_row; }
+};
+template <>
+struct TableT<true> {
+    using type = __nv_bfloat16;
+    static __device__ __forceinline__ const __nv_bfloat16 *neg() { return reinterpret_cast<const __nv_bfloat16 *>(g_neg_row_h); }
+};
 
 template <int C, int NS>
 struct TcLayout {
@@ -260,9 +278,11 @@ struct TcShape {
     static constexpr int kMinBlocks = C <= 32 ? CF_MB32 : C <= 64 ? CF_MB64 : 1;
 };
 
-template <int C, int NS>
+template <int C, int NS, bool TH = false>
 __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks) k_fusion_tc(const TcParams p)
 {
+    using TT = typename TableT<TH>::type;   // fp32 tables, or bf16 tables in CF_MODE_BF16_TABLES (NS == 1)
+    const TT *const g_neg = TableT<TH>::neg();
     using L = TcLayout<C, NS>;
     constexpr int G = TcShape<C>::G, EW = kEW;
     constexpr int NT = kTile * G;
@@ -424,10 +444,10 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
     // one item = 8 rows x 32 channels per warp: lane (r8, u) turns 8 channels of one neighbour row into two 16-byte
     // operand units (hi, lo).  Per item and lane: 2 LDS, 2 LDG.128, 8 FFMA2, 8 F2FP, 8 unpack, 4 FADD2, 2 STS.128 --
     // rows without a k-th neighbour read a row of -1e30, which the fused ReLU turns into zeros.
-    auto gather = [&](const float *Tc, const float *neg, uint32_t idx_addr, float *t) {   // t[8]
+    auto gather = [&](const TT *Tc, const TT *neg, uint32_t idx_addr, float *t) {   // t[8]
         const int32_t pr = (int32_t)tc::lds_u32(idx_addr);
         // one 256-bit load per lane: the 4 lanes of a row fetch one full 128-byte line in a single request
-        tc::ldg_nc_f32x8(pr >= 0 ? Tc + (size_t)pr * C : neg, t);
+        tc::ldg_row8(pr >= 0 ? Tc + (size_t)pr * C : neg, t);
     };
     auto build = [&](const float *t, const float4 &ctr, uint32_t dst_addr) {
         const float2 cxx = make_float2(ctr.x, ctr.y), cyy = make_float2(ctr.z, ctr.w);
@@ -503,7 +523,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             if (grp == 0 && has_next) ncell = header_cell(nb, nq);
             if (R == 0 && grp == 0 && has_next) header_fill(nb, ncell, par ^ 1);
 
-            const float *Tb = p.T + (size_t)b * p.N * C;
+            const TT *Tb = reinterpret_cast<const TT *>(p.T) + (size_t)b * p.N * C;
             const uint32_t idx0 = sidx_addr + (uint32_t)((par * K * kTile + rg0 * 8 + r8) * 4);
             const uint32_t ctr0 = sctr_addr + (uint32_t)((par * kTile + rg0 * 8 + r8) * 16);
             const uint32_t dst0 = sA_addr + tc::unit_offset(r8, ku, kc_units) + (uint32_t)(rg0 * kc_units * 128);
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                 }
             };
             if (kPipe && R > 0) {
-                const float *Tc = Tb + ku * 8, *neg = g_neg_row + ku * 8;
+                const TT *Tc = Tb + ku * 8, *neg = g_neg + ku * 8;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gather(Tc, neg, idx0 + i * kStep * 32, tv + 8 * i);
             }
@@ -538,7 +558,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             constexpr int kMaxItems = (16 + kStep - 1) / kStep;
             float pv[kPipe2 ? kMaxItems * 8 : 1];
             auto gather_chunk = [&](int k, int ch) {
-                const float *Tc = Tb + ch * KC + ku * 8, *neg = g_neg_row + ch * KC + ku * 8;
+                const TT *Tc = Tb + ch * KC + ku * 8, *neg = g_neg + ch * KC + ku * 8;
 #pragma unroll
                 for (int m = 0; m < kMaxItems; ++m)
                     if (rg0 + m * kStep < 16) gather(Tc, neg, idx0 + (uint32_t)(k * kTile * 4 + m * kStep * 32), pv + 8 * m);
@@ -573,7 +593,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         }
                     } else {
                         load_offset_weights(ch);
-                        const float *Tc = Tb + ch * KC + ku * 8, *neg = g_neg_row + ch * KC + ku * 8;
+                        const TT *Tc = Tb + ch * KC + ku * 8, *neg = g_neg + ch * KC + ku * 8;
 #pragma unroll 1
                         for (int rg = rg0; rg < 16; rg += 2 * kStep) {   // pairs of items: both gathers in flight
                             float ta[8], tb[8];
@@ -593,7 +613,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         // issue, so they get the barrier skew and the issue time as extra lead and the issuing warp does not lag
                         // (C = 32: 266 -> 260 us out of place, 184 -> 178 us in place; neutral at C = 64, where it adds spills)
                         if (k + 1 < R) {
-                            const float *Tc = Tb + ku * 8, *neg = g_neg_row + ku * 8;
+                            const TT *Tc = Tb + ku * 8, *neg = g_neg + ku * 8;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) gather(Tc, neg, idxk + kTile * 4 + i * kStep * 32, tv + 8 * i);
                         } else {
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
                         if (k == 0 && grp == 0 && has_next) header_fill(nb, ncell, par ^ 1);
                         if (k + 1 < R) {
                             if (kPipe && !kGatherEarly) {
-                                const float *Tc = Tb + ku * 8, *neg = g_neg_row + ku * 8;
+                                const TT *Tc = Tb + ku * 8, *neg = g_neg + ku * 8;
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) gather(Tc, neg, idxk + kTile * 4 + i * kStep * 32, tv + 8 * i);
                             }
@@ -814,9 +834,11 @@ struct SkLayout {
     static constexpr int kTmemCols = tmem_cols_for(3 * C);          // two accumulators + the pooled sum
 };
 
-template <int C, int NS>
+template <int C, int NS, bool TH = false>
 __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks) k_fusion_sk(const TcParams p)
 {
+    using TT = typename TableT<TH>::type;
+    const TT *const g_neg = TableT<TH>::neg();
     using L = SkLayout<C, NS>;
     constexpr int G = TcShape<C>::G, EW = kEW;
     constexpr int NT = kTile * G, NW = NT / 32;
@@ -985,7 +1007,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
             int32_t ncell = -1;
             if (grp == 0 && has_next) ncell = header_cell(nb, nq);
 
-            const float *Tc = p.T + (size_t)b * p.N * C + ku * 8, *neg = g_neg_row + ku * 8;
+            const TT *Tc = reinterpret_cast<const TT *>(p.T) + (size_t)b * p.N * C + ku * 8, *neg = g_neg + ku * 8;
             const uint32_t idx0 = sidx_addr + (uint32_t)((par * K * kTile + rg0 * 8 + r8) * 4);
             const uint32_t ctr0 = sctr_addr + (uint32_t)((par * kTile + rg0 * 8 + r8) * 8);
             const uint32_t dst0 = sA_addr + tc::unit_offset(r8, ku, kc_units) + (uint32_t)(rg0 * kc_units * 128);
@@ -995,7 +1017,7 @@ __global__ void __launch_bounds__(kTile * TcShape<C>::G, TcShape<C>::kMinBlocks)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int32_t pr = (int32_t)tc::lds_u32(idx0 + (uint32_t)(k * kTile * 4 + i * kStep * 32));
-                    tc::ldg_nc_f32x8(pr >= 0 ? Tc + (size_t)pr * C : neg, tv + 8 * i);
+                    tc::ldg_row8(pr >= 0 ? Tc + (size_t)pr * C : neg, tv + 8 * i);
                 }
             };
             auto prefetch_bev = [&]() {
@@ -1360,18 +1382,22 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxScales = 8, kMaxChunks = 24;
 constexpr int kMultiThreads = 544;   // 16 worker warps + the MMA issuer warp
-constexpr int kStageGroup = kTile * 128;              // one 128-row x 32-column fp32 block (rows of 128 bytes, SWIZZLE_128B)
+constexpr int kStageGroup = kTile * 128;              // one staged block: 128 rows of 128 bytes (32 fp32 / 64 bf16 columns), SWIZZLE_128B
 // Per split count: output columns per chunk (UMMA N) and whether full tiles are staged for TMA stores.  The staged path pays
 // when the tables leave for DRAM (bf16 mode at configs[2]: 2.5 GB per step); with two splits the operands leave no room
 // for the staging sets, and at configs[1] the tables stay in L2 where the direct stores were measured faster (114 vs 125 us).
-template <int NS>
+// TH (CF_MODE_BF16_TABLES): the tables are written as bf16 -- half the bytes per column, so a 128-column chunk fits the
+// same two staged blocks.
+template <int NS, bool TH = false>
 struct MultiShape {
-    static constexpr int kChunkW = NS == 2 ? 128 : 64;
+    static_assert(!TH || NS == 1, "bf16 tables belong to the bf16 operand mode");
+    static constexpr int kChunkW = NS == 2 || TH ? 128 : 64;
+    static constexpr int kGroupCols = TH ? 64 : 32;   // columns of one staged block
     static constexpr int kWBufs = 2;       // weight ring: a chunk is requested kWBufs chunks before its MMAs
                                            // (4 buffers and 3 staging sets measured the same 0.99 ms at configs[2]: the kernel is
                                            // bound by the DRAM write rate, 2.5 GB of tables at ~2.5 TB/s + 0.5 GB of reads)
     static constexpr bool kStaged = NS == 1;
-    static constexpr int kStageSet = (kChunkW / 32) * kStageGroup;   // the staged output of one chunk
+    static constexpr int kStageSet = (kChunkW / kGroupCols) * kStageGroup;   // the staged output of one chunk
     static constexpr int kStageSets = 2;   // a staged block has kStageSets - 1 chunk iterations to be read by the TMA engine
     static constexpr int kStageBytes = kStaged ? kStageSets * kStageSet : 0;
 };
@@ -1400,15 +1426,16 @@ struct Mlp1Maps {
 // lines without passing the LSU again.  (A thread owns one ROW of the accumulator, so direct global stores touch 32 lines per
 // instruction; that made the kernel LSU-bound at a third of the HBM write rate.)  The last, partial tile of a frame stores
 // directly so that rows past num_points stay untouched.
-template <int NS>
+template <int NS, bool TH = false>
 __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp1MultiParams p, const __grid_constant__ Mlp1Maps maps)
 {
+    using MS = MultiShape<NS, TH>;
     // warps 0-15: workers (operand build, epilogues; 4 threads per row split the columns of a chunk);
     // warp 16: one elected lane streams the weight chunks (two cp.async.bulk per chunk: TMA engine, mbarrier complete_tx) and
     // issues the MMAs (descriptors in uniform registers), so the tcgen05.mma of a chunk never sit in front of an epilogue
     constexpr int NT = kMultiThreads - 32, NW = NT / 32, kIssuer = NT, kColGroups = NT / kTile;
-    constexpr int kChunkW = MultiShape<NS>::kChunkW, kStageSet = MultiShape<NS>::kStageSet, kStageBytes = MultiShape<NS>::kStageBytes;
-    constexpr uint32_t kWBufs = MultiShape<NS>::kWBufs, kStageSets = MultiShape<NS>::kStageSets;
+    constexpr int kChunkW = MS::kChunkW, kStageSet = MS::kStageSet, kStageBytes = MS::kStageBytes, kGroupCols = MS::kGroupCols;
+    constexpr uint32_t kWBufs = MS::kWBufs, kStageSets = MS::kStageSets;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar[2], wbar[kWBufs];   // MMAs of a chunk complete; weights of a chunk have landed
     __shared__ uint32_t tmem_slot;
@@ -1471,8 +1498,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     auto flush_pending = [&]() {
         if (pend_j >= 0 && tid == 0) {
             const int s = p.chunk_scale[pend_j], n0 = p.chunk_n0[pend_j], len = p.chunk_len[pend_j];
-            for (int g = 0; g < len / 32; ++g)
-                tc::tma_store_3d(&maps.m[s], n0 + g * 32, pend_m0, pend_b, stage_addr + pend_set * kStageSet + g * kStageGroup);
+            for (int g = 0; g * kGroupCols < len; ++g)   // (a 32-column scale fills half a bf16 block: the map clips at C)
+                tc::tma_store_3d(&maps.m[s], n0 + g * kGroupCols, pend_m0, pend_b, stage_addr + pend_set * kStageSet + g * kStageGroup);
             tc::bulk_commit();
         }
         pend_j = -1;
@@ -1490,7 +1517,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         const int32_t m0 = (int32_t)(tile - (int64_t)b * p.tiles_per_frame) * kTile;
         const int32_t n_pts = valid_points(p.num_points, b, p.N);
         if (m0 >= n_pts) continue;  // uniform across the CTA
-        const bool full = MultiShape<NS>::kStaged && p.tma_out && m0 + kTile <= n_pts;
+        const bool full = MS::kStaged && p.tma_out && m0 + kTile <= n_pts;
         // ---- A tile, once for all scales (same lane mapping as k_point_mlp1_tc).  The feature rows stream from DRAM:
         // the loads of a batch of items are all issued before the first one is split and stored ------------------------
         const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;
@@ -1534,7 +1561,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
             const int s = p.chunk_scale[j], n0 = p.chunk_n0[j], len = p.chunk_len[j], C = p.C[s];
             const float4 *f = reinterpret_cast<const float4 *>(sF + p.foff[s]);
             const uint32_t acc = tmem_base + buf * kChunkW + lane_off;
-            float *trow = p.T[s] + ((size_t)b * p.N + m) * C + n0;
+            float *trow = p.T[s] + (TH ? 0 : ((size_t)b * p.N + m) * C + n0);
+            __nv_bfloat16 *trow_h = reinterpret_cast<__nv_bfloat16 *>(p.T[s]) + ((size_t)b * p.N + m) * C + n0;
             uint8_t *srow = sStage + en * kStageSet + row * 128;
 #pragma unroll 1
             for (int c = half * 16; worker && c < len; c += 16 * kColGroups) {
@@ -1549,7 +1577,17 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
                             const float4 w = f[n0 + c + q8 * 8 + i];
                             o[i] = z[q8 * 8 + i] + (w.y * px + w.z * py + w.w * pz) + w.x;
                         }
-                        if (full) {   // 16-byte chunk q of the row's 128-byte line sits at q ^ (row & 7)
+                        if (TH) {   // 8 columns -> one 16-byte chunk of bf16 (round to nearest even)
+                            const uint4 h = make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]),
+                                                       tc::pack_bf16x2(o[6], o[7]));
+                            if (full) {
+                                uint8_t *grp = srow + (c >> 6) * kStageGroup;
+                                const int q = ((c & 63) >> 3) + q8;
+                                *reinterpret_cast<uint4 *>(grp + ((q ^ (row & 7)) << 4)) = h;
+                            } else {
+                                *reinterpret_cast<uint4 *>(trow_h + c + q8 * 8) = h;
+                            }
+                        } else if (full) {   // 16-byte chunk q of the row's 128-byte line sits at q ^ (row & 7)
                             uint8_t *grp = srow + (c >> 5) * kStageGroup;
                             const int q = ((c & 31) >> 2) + q8 * 2;
                             *reinterpret_cast<float4 *>(grp + (((q) ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
@@ -1726,7 +1764,7 @@ int resident_ctas(Kern kern, int threads, int smem, int tmem_cols, int *regs_cac
     return CF_OK;
 }
 
-template <int C, int NS>
+template <int C, int NS, bool TH = false>
 int launch_tc(const TcParams &p, cudaStream_t st)
 {
     using L = TcLayout<C, NS>;
@@ -1734,23 +1772,23 @@ int launch_tc(const TcParams &p, cudaStream_t st)
     const int smem = L::smem_bytes(p.K);
     static int attr_bytes = 0, regs = 0;
     if (smem > attr_bytes) {
-        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_tc<C, NS, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                            "k_fusion_tc smem attribute"));
         attr_bytes = smem;
     }
     int per_sm = 1;
-    CF_TRY(resident_ctas(k_fusion_tc<C, NS>, NT, smem, L::kTmemCols, &regs, &per_sm));
+    CF_TRY(resident_ctas(k_fusion_tc<C, NS, TH>, NT, smem, L::kTmemCols, &regs, &per_sm));
     per_sm = std::max(1, per_sm);
     if (tuning().max_ctas > 0) per_sm = std::max(1, std::min(per_sm, tuning().max_ctas));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
     if (tuning().debug_launch) fprintf(stderr, "k_fusion_tc<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
-    k_fusion_tc<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
+    k_fusion_tc<C, NS, TH><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
 
 // The double-buffered kernel (k_fusion_sk) is used when its shared memory fits and it keeps the residency of k_fusion_tc;
 // returns CF_ERR_UNSUPPORTED (nothing launched) otherwise.  CF_NO_SKEW=1 forces k_fusion_tc (A/B measurements).
-template <int C, int NS>
+template <int C, int NS, bool TH = false>
 int launch_sk(const TcParams &p, cudaStream_t st)
 {
     using L = SkLayout<C, NS>;
@@ -1760,18 +1798,18 @@ int launch_sk(const TcParams &p, cudaStream_t st)
     if (smem > 227 * 1024 || tuning().no_skew) return CF_ERR_UNSUPPORTED;
     static int attr_bytes = 0, regs = 0, regs0 = 0;
     int per_sm = 0, per_sm0 = 0;
-    CF_TRY(resident_ctas(k_fusion_sk<C, NS>, NT, smem, L::kTmemCols, &regs, &per_sm));
-    CF_TRY(resident_ctas(k_fusion_tc<C, NS>, NT, L0::smem_bytes(p.K), L0::kTmemCols, &regs0, &per_sm0));
+    CF_TRY(resident_ctas(k_fusion_sk<C, NS, TH>, NT, smem, L::kTmemCols, &regs, &per_sm));
+    CF_TRY(resident_ctas(k_fusion_tc<C, NS, TH>, NT, L0::smem_bytes(p.K), L0::kTmemCols, &regs0, &per_sm0));
     if (per_sm < 1 || per_sm < per_sm0) return CF_ERR_UNSUPPORTED;
     if (smem > attr_bytes) {
-        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_sk<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+        CF_TRY(cuda_status(cudaFuncSetAttribute(k_fusion_sk<C, NS, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                            "k_fusion_sk smem attribute"));
         attr_bytes = smem;
     }
     if (tuning().max_ctas > 0) per_sm = std::max(1, std::min(per_sm, tuning().max_ctas));
     const int64_t grid = std::min<int64_t>(p.tiles_total, (int64_t)sm_count() * per_sm);
     if (tuning().debug_launch) fprintf(stderr, "k_fusion_sk<%d,%d>: %d CTAs/SM grid %lld smem %d\n", C, NS, per_sm, (long long)grid, smem);
-    k_fusion_sk<C, NS><<<(unsigned)grid, NT, smem, st>>>(p);
+    k_fusion_sk<C, NS, TH><<<(unsigned)grid, NT, smem, st>>>(p);
     return CF_OK;
 }
 
@@ -1833,7 +1871,7 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     const bool compact = ceil_div64(n_cells, kTile) * B >= min_tiles;
     // fine scales (many more tiles than SMs): segment tiles, all neighbour slots in one MMA batch (cf_fusion_seg.cu); its
     // lists live where the cell lists of the kernels below would
-    if (compact && tuning().seg) {
+    if (compact && tuning().seg && mode != CF_MODE_BF16_TABLES) {
         const int rc = fusion_seg(d_bev, d_T, d_knn, B, N, C, H, W, K, x0, y0, dx, dy, d_W1, Ci, d_b2, d_b3, d_out, mode, img2,
                                   img3, cell_count, st);
         if (rc != CF_ERR_UNSUPPORTED) return rc;
@@ -1854,14 +1892,16 @@ int fusion_tc(const float *d_bev, const float *d_T, const int32_t *d_knn, int32_
     p.cell_count = cell_count;
     p.copy_dead = compact && d_out != d_bev;
     int rc = CF_ERR_UNSUPPORTED;
-#define CF_TC_CASE(c)                                                          \
-    case c:                                                                    \
-        rc = NS == 2 ? launch_tc<c, 2>(p, st) : launch_tc<c, 1>(p, st);        \
+    const bool th = mode == CF_MODE_BF16_TABLES;   // d_T holds bf16 rows
+#define CF_TC_CASE(c)                                                                                          \
+    case c:                                                                                                    \
+        rc = NS == 2 ? launch_tc<c, 2>(p, st) : th ? launch_tc<c, 1, true>(p, st) : launch_tc<c, 1>(p, st);    \
         break;
-#define CF_SK_CASE(c)                                                          \
-    case c:                                                                    \
-        rc = NS == 2 ? launch_sk<c, 2>(p, st) : launch_sk<c, 1>(p, st);        \
-        if (rc == CF_ERR_UNSUPPORTED) rc = NS == 2 ? launch_tc<c, 2>(p, st) : launch_tc<c, 1>(p, st); \
+#define CF_SK_CASE(c)                                                                                          \
+    case c:                                                                                                    \
+        rc = NS == 2 ? launch_sk<c, 2>(p, st) : th ? launch_sk<c, 1, true>(p, st) : launch_sk<c, 1>(p, st);    \
+        if (rc == CF_ERR_UNSUPPORTED)                                                                          \
+            rc = NS == 2 ? launch_tc<c, 2>(p, st) : th ? launch_tc<c, 1, true>(p, st) : launch_tc<c, 1>(p, st); \
         break;
     switch (C) {
         // measured on B200 (profiles/README.md): the double-buffered kernel wins where the MMAs of a round are long
@@ -1925,9 +1965,9 @@ int point_mlp1_tc(const float *d_feat, const float *d_points, const int64_t *d_n
     return launch_status("cf_point_mlp1 (tcgen05)");
 }
 
-// 3-D tensor map over a table T (B, N, C) fp32: x = channel (fastest), y = point, z = frame; box 32 x 128 x 1 with the
+// 3-D tensor map over a table T (B, N, C) fp32 (or bf16): x = channel (fastest), y = point, z = frame; box 32 (64) x 128 x 1 with the
 // 128-byte swizzle (the layout the epilogue stages).  Rows past N are clipped by the TMA engine.
-static int make_table_map(CUtensorMap *tm, float *base, int32_t C, int32_t N, int32_t B)
+static int make_table_map(CUtensorMap *tm, float *base, int32_t C, int32_t N, int32_t B, bool th)
 {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1941,11 +1981,12 @@ static int make_table_map(CUtensorMap *tm, float *base, int32_t C, int32_t N, in
         fn = (EncodeTiledFn)f;
     }
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)kTile, 1};
+    const cuuint64_t el_bytes = th ? 2 : 4;
+    const cuuint64_t strides[2] = {(cuuint64_t)C * el_bytes, (cuuint64_t)N * C * el_bytes};
+    const cuuint32_t box[3] = {th ? 64u : 32u, (cuuint32_t)kTile, 1};   // rows of 128 bytes
     const cuuint32_t el[3] = {1, 1, 1};
-    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = fn(tm, th ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, el,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_LAUNCH, "cuTensorMapEncodeTiled failed for a (%d, %d, %d) table (%d)", B, N, C, (int)r);
     return CF_OK;
 }
@@ -1961,8 +2002,9 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     Mlp1MultiParams p;
     p.feat = d_feat; p.points = d_points; p.num_points = d_num_points;
     p.B = B; p.N = N; p.Ci = Ci; p.tiles_per_frame = (N + kTile - 1) / kTile; p.n_scales = n_scales;
-    const int chunk_w = NS == 2 ? MultiShape<2>::kChunkW : MultiShape<1>::kChunkW;
-    const int stage_bytes = NS == 2 ? MultiShape<2>::kStageBytes : MultiShape<1>::kStageBytes;
+    const bool th = mode == CF_MODE_BF16_TABLES;
+    const int chunk_w = NS == 2 ? MultiShape<2>::kChunkW : th ? MultiShape<1, true>::kChunkW : MultiShape<1>::kChunkW;
+    const int stage_bytes = NS == 2 ? MultiShape<2>::kStageBytes : th ? MultiShape<1, true>::kStageBytes : MultiShape<1>::kStageBytes;
     int chunks = 0, foff = 0;
     for (int s = 0; s < n_scales; ++s) {
         const int C = h_C[s];
@@ -1985,8 +2027,8 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     p.tma_out = stage_bytes > 0;
     for (int s = 0; s < n_scales; ++s)
         if (((uintptr_t)h_T[s] & 15u) != 0) p.tma_out = 0;
-    for (int s = 0; s < n_scales && p.tma_out; ++s) CF_TRY(make_table_map(&maps.m[s], h_T[s], h_C[s], N, B));
-    auto kern = NS == 2 ? k_point_mlp1_multi<2> : k_point_mlp1_multi<1>;
+    for (int s = 0; s < n_scales && p.tma_out; ++s) CF_TRY(make_table_map(&maps.m[s], h_T[s], h_C[s], N, B, th));
+    auto kern = NS == 2 ? k_point_mlp1_multi<2> : th ? k_point_mlp1_multi<1, true> : k_point_mlp1_multi<1>;
     CF_TRY(cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "k_point_mlp1_multi smem attribute"));
     const int64_t tiles = (int64_t)p.tiles_per_frame * B;

@@ -315,6 +315,20 @@ __device__ __forceinline__ void ldg_nc_f32x8(const float *p, float *v)
         : "l"(p));
 }
 
+// 8 consecutive channels of a layer-1 table row as fp32: fp32 tables (one 256-bit load) or bf16 tables (one 128-bit load,
+// bf16 -> fp32 is a shift)
+__device__ __forceinline__ void ldg_row8(const float *p, float *v) { ldg_nc_f32x8(p, v); }
+__device__ __forceinline__ void ldg_row8(const __nv_bfloat16 *p, float *v)
+{
+    uint32_t r[4];
+    asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(r[i] << 16);
+        v[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u);
+    }
+}
+
 // the same load pinned in program order (volatile asm): keeps a software-pipelined gather where it was written instead of
 // letting the scheduler hoist every load of a tile to its top (register pressure)
 __device__ __forceinline__ void ldg_nc_f32x8_pinned(const float *p, float *v)

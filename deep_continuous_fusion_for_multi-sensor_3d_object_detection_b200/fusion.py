@@ -107,11 +107,11 @@ class FrameContext:
         dev = self.points.device
         Ci = self.feat.shape[2]
         multi = (len(layers) > 1 and len(layers) <= 8 and Ci % 32 == 0 and Ci <= 128 and len({l.mode for l in layers}) == 1
-                 and layers[0].mode in ("fp32", "bf16") and all(l.c_bev % 32 == 0 for l in layers)
+                 and layers[0].mode in ("fp32", "bf16", "bf16t") and all(l.c_bev % 32 == 0 for l in layers)
                  and sum(-(-l.c_bev // 128) for l in layers) <= 16)
         if multi:
             # one launch for every scale: the point features are packed into the tensor-core operand once
-            Ts = [torch.empty((self.B, self.N, l.c_bev), dtype=torch.float32, device=dev) for l in layers]
+            Ts = [torch.empty((self.B, self.N, l.c_bev), dtype=ops.table_dtype(l.mode), device=dev) for l in layers]
             packed = [l._packed.w1(l.fc1.weight.detach(), l.mode) for l in layers]   # packs on the current (main) stream if stale
             st = streams[1]
             st.wait_stream(main)
@@ -124,7 +124,7 @@ class FrameContext:
                 T.record_stream(st)   # allocated on main's pool, written on st: the block must not be reused before st is done
                 self._tables[id(l)] = (T, ev)
         for layer, st in zip([] if multi else layers, streams[1:]):
-            T = torch.empty((self.B, self.N, layer.c_bev), dtype=torch.float32, device=dev)
+            T = torch.empty((self.B, self.N, layer.c_bev), dtype=ops.table_dtype(layer.mode), device=dev)
             packed = layer._packed.w1(layer.fc1.weight, layer.mode)   # packs on the current (main) stream if stale
             st.wait_stream(main)
             with torch.cuda.stream(st), torch.no_grad():
@@ -306,8 +306,8 @@ class ContinuousFusion(nn.Module):
         super().__init__()
         if not (1 <= k <= 16):
             raise ValueError("k must be in [1, 16]")
-        if mode not in ("fp32", "bf16", "simt"):
-            raise ValueError(f"mode must be 'fp32', 'bf16' or 'simt', got {mode!r}")
+        if mode not in ("fp32", "bf16", "simt", "bf16t"):
+            raise ValueError(f"mode must be 'fp32', 'bf16', 'bf16t' (bf16 with bf16 tables, inference only) or 'simt', got {mode!r}")
         if c_bev % 16 or not (16 <= c_bev <= 256):
             raise ValueError("c_bev must be a multiple of 16 in [16, 256]")
         if mode != "simt" and c_bev not in TENSOR_CORE_WIDTHS:
@@ -347,6 +347,9 @@ class ContinuousFusion(nn.Module):
                 self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias, self._packed)
         needs_grad = torch.is_grad_enabled() and (bev.requires_grad or frames.feat.requires_grad or
                                                   any(p.requires_grad for p in self.parameters()))
+        if needs_grad and self.mode == "bf16t":
+            raise RuntimeError("ContinuousFusion: mode 'bf16t' stores the layer-1 tables as bf16 and is inference only; "
+                               "train in 'fp32' or 'bf16' (same weights) and switch layer.mode for deployment")
         if needs_grad:
             # a table launched ahead by FrameContext.precompute is only an intermediate of this Function: its gradient
             # path (feat, W1, b1) is the Function's own backward, so it can be used here as well

@@ -35,7 +35,7 @@ FUSION_DEFAULTS = {
     "fusion_scales": (1,),         # residual groups after which the layer is applied, 1..5 (A11)
     "fusion_image_channels": 128,  # C_img of the camera feature map
     "fusion_image_stride": 4,      # camera map is (image_height/stride, image_width/stride)
-    "fusion_mlp_mode": "fp32",     # "fp32" | "bf16" | "simt" (A12)
+    "fusion_mlp_mode": "fp32",     # "fp32" | "bf16" | "bf16t" (bf16 + bf16 tables, inference only) | "simt" (A12)
     "fusion_bucket_size": 0.5,     # metres, K-1 grid pitch
 }
 

@@ -248,8 +248,21 @@ class PackedWeights:
         return self._buf23
 
 
+def _table_check(t, name, m, shape):
+    """A caller-supplied table must have the mode's dtype: the kernels take raw pointers."""
+    want = table_dtype(m)
+    if t.dtype != want or tuple(t.shape) != tuple(shape) or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError(f"{name}: expected a contiguous CUDA {want} tensor of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+
+
+def table_dtype(mode):
+    """dtype of the layer-1 tables T in `mode`: bf16 in "bf16t" (CF_MODE_BF16_TABLES), fp32 otherwise."""
+    m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+    return torch.bfloat16 if m == _lib.MODE_BF16_TABLES else torch.float32
+
+
 def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspace=None, packed=None):
-    """K-4a.  T (B,N,C) = feat W1[:, :Ci]^T + points W1[:, Ci:]^T + b1."""
+    """K-4a.  T (B,N,C) = feat W1[:, :Ci]^T + points W1[:, Ci:]^T + b1  (fp32; bf16 rows in mode "bf16t")."""
     lib = load()
     feat = _contig(feat, "feat", torch.float32, 3)
     points = _contig(points, "points", torch.float32, 3)
@@ -264,7 +277,8 @@ def point_mlp1(feat, points, num_points, W1, b1, mode="fp32", out=None, workspac
     if need and (workspace is None or workspace.numel() < need):
         workspace = torch.empty((need,), dtype=torch.uint8, device=feat.device)
     if out is None:
-        out = torch.empty((B, N, C_out), dtype=torch.float32, device=feat.device)
+        out = torch.empty((B, N, C_out), dtype=table_dtype(m), device=feat.device)
+    _table_check(out, "point_mlp1: out", m, (B, N, C_out))
     check(lib.cf_point_mlp1(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, C_out, ptr(W1), ptr(b1), ptr(out), m,
                             ptr(packed), ptr(workspace) if need else None, stream_ptr()), "cf_point_mlp1")
     return out
@@ -287,9 +301,11 @@ def point_mlp1_multi(feat, points, num_points, W1s, b1s, packeds, mode="fp32", o
             raise ValueError(f"W1/b1: expected (C,{Ci + 3})/(C,), got {tuple(w.shape)}/{tuple(b.shape)}")
     if len(b1s) != n or len(packeds) != n or any(pk is None for pk in packeds):
         raise ValueError("point_mlp1_multi: one W1, b1 and packed image per scale")
-    if outs is None:
-        outs = [torch.empty((B, N, w.shape[0]), dtype=torch.float32, device=feat.device) for w in W1s]
     m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+    if outs is None:
+        outs = [torch.empty((B, N, w.shape[0]), dtype=table_dtype(m), device=feat.device) for w in W1s]
+    for t, w in zip(outs, W1s):
+        _table_check(t, "point_mlp1_multi: outs", m, (B, N, w.shape[0]))
     arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
     hC = (C.c_int32 * n)(*[int(w.shape[0]) for w in W1s])
     check(lib.cf_point_mlp1_multi(ptr(feat), ptr(points), ptr(num_points), B, N, Ci, n, hC, arr(W1s), arr(b1s), arr(outs), m,
@@ -309,7 +325,7 @@ def fusion_fwd(bev, T, knn_idx, geom, W1, W2, b2, W3, b3, mode="fp32", out=None,
         if out.data_ptr() == bev.data_ptr() and not bev.is_contiguous():
             raise ValueError("fusion_fwd: in-place operation (out is bev) needs a contiguous (dense NCHW) map")
     bev = _contig(bev, "bev", torch.float32, 4)
-    T = _contig(T, "T", torch.float32, 3)
+    T = _contig(T, "T", table_dtype(mode), 3)
     knn_idx = _contig(knn_idx, "knn_idx", torch.int32, 4)
     B, Cc, H, W = bev.shape
     N = T.shape[1]

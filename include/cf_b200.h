@@ -45,6 +45,10 @@ extern "C" {
 #define CF_MODE_FP32 0      /* fp32-accurate: split-bf16 x3 on tcgen05 (or FFMA), fp32 accumulate */
 #define CF_MODE_BF16 1      /* bf16 operands on tcgen05, fp32 accumulate / pool / add            */
 #define CF_MODE_FP32_SIMT 2 /* CUDA-core FFMA path (bring-up / cross-check path)                  */
+#define CF_MODE_BF16_TABLES 3 /* CF_MODE_BF16 with the layer-1 tables T stored as bf16 (inference only):
+                               * cf_point_mlp1 / cf_point_mlp1_multi write bf16 rows into d_T / h_T[s], cf_fusion_fwd
+                               * reads them; halves the table traffic, doubles the rounding error of CF_MODE_BF16
+                               * (still within its 1e-2 tolerance); cf_fusion_bwd rejects it                  */
 
 CF_API int cf_abi_version(void);
 CF_API const char *cf_last_error(void);

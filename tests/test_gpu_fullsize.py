@@ -61,6 +61,12 @@ def test_cfg2_full_frame_bf16(dcf, oracle):
     ref_outs, ref_knns = oracle_fusion(oracle, wl)
     outs, knns = cuda_fusion(dcf, wl, "bf16")
     _check(wl, outs, knns, ref_outs, ref_knns, 1e-2, "cfg2")
+    # the same frame with the layer-1 tables stored as bf16 (CF_MODE_BF16_TABLES): same tolerance, out of place and in place
+    outs_t, knns_t = cuda_fusion(dcf, wl, "bf16t")
+    _check(wl, outs_t, knns_t, ref_outs, ref_knns, 1e-2, "cfg2 bf16 tables")
+    outs_ti, _ = cuda_fusion(dcf, wl, "bf16t", inplace=True)
+    for sc, x, y in zip(wl["scales"], outs_t, outs_ti):
+        assert np.array_equal(x, y), f"group {sc['group']}: bf16 tables, in place != out of place"
 
 
 def test_segment_kernel_opt_in_matches_oracle():

@@ -94,6 +94,68 @@ def test_point_mlp1_multi_equals_per_scale_calls(dcf, mode):
         assert one[0].abs().max() > 0 and float(tm[1].abs().max()) == 0.0 and float(tm[2, 517:].abs().max()) == 0.0
 
 
+def test_bf16_tables_layer1_is_the_rounded_fp32_table(dcf):
+    """CF_MODE_BF16_TABLES ("bf16t"): cf_point_mlp1_multi writes exactly round-to-nearest-even bf16 of the CF_MODE_BF16 table
+    (full tiles leave through TMA stores, the partial tile of a frame through direct stores), rows past num_points stay
+    untouched, and the single-scale entry point gives the same rows."""
+    torch.manual_seed(23)
+    B, N, Ci = 3, 1000, 128
+    feat = torch.randn(B, N, Ci, device="cuda")
+    pts = torch.randn(B, N, 3, device="cuda") * 20
+    cnt = torch.tensor([1000, 0, 517], dtype=torch.int64, device="cuda")
+    Cs = [32, 64, 128, 192, 256]
+    W1s = [torch.randn(c, Ci + 3, device="cuda") * 0.1 for c in Cs]
+    b1s = [torch.randn(c, device="cuda") for c in Cs]
+    pk = [dcf.ops.PackedWeights().w1(w, "bf16") for w in W1s]
+    pkt = [dcf.ops.PackedWeights().w1(w, "bf16t") for w in W1s]
+    ref = dcf.ops.point_mlp1_multi(feat, pts, cnt, W1s, b1s, pk, mode="bf16", outs=[torch.zeros(B, N, c, device="cuda") for c in Cs])
+    got = dcf.ops.point_mlp1_multi(feat, pts, cnt, W1s, b1s, pkt, mode="bf16t",
+                                   outs=[torch.zeros(B, N, c, device="cuda", dtype=torch.bfloat16) for c in Cs])
+    torch.cuda.synchronize()
+    for r, g, w, b, p, c in zip(ref, got, W1s, b1s, pkt, Cs):
+        assert g.dtype == torch.bfloat16 and torch.equal(g, r.to(torch.bfloat16)), f"C={c}"
+        assert float(g[1].abs().max()) == 0.0 and float(g[2, 517:].abs().max()) == 0.0 and float(g[0].abs().max()) > 0
+        one = dcf.ops.point_mlp1(feat, pts, cnt, w, b, mode="bf16t", packed=p, out=torch.zeros(B, N, c, device="cuda", dtype=torch.bfloat16))
+        assert torch.equal(one, g), f"C={c}: single-scale entry point"
+    with pytest.raises(ValueError, match="bfloat16"):
+        dcf.ops.point_mlp1_multi(feat, pts, cnt, W1s, b1s, pkt, mode="bf16t", outs=[torch.zeros(B, N, c, device="cuda") for c in Cs])
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 31), ("yaml", 32)])
+def test_bf16_tables_fused_layer_equals_bf16_mode_on_the_rounded_table(dcf, name, seed):
+    """The fused kernels of "bf16t" differ from "bf16" only in how a table row is loaded: fed the same (bf16-representable)
+    rows they must give the same bits, at every scale width, out of place and in place."""
+    wl = dcf.synthetic.make_workload(name, seed=seed)
+    pts, cnt, img = dev(wl["points"]), dev(wl["num_points"]), dev(wl["img_feat"])
+    frames = dcf.prepare_frames(pts, cnt, img, config=wl["config"], calib=wl["calib"])
+    for sc in wl["scales"]:
+        w1, b1, w2, b2, w3, b3 = [dev(w) for w in sc["weights"]]
+        bev = dev(sc["bev"])
+        knn = frames.knn(sc["H"], sc["W"], sc["geom"], wl["radius"], wl["k"])
+        Th = dcf.ops.point_mlp1(frames.feat, pts, cnt, w1, b1, mode="bf16t")
+        assert Th.dtype == torch.bfloat16
+        a, _ = dcf.ops.fusion_fwd(bev, Th, knn, sc["geom"], w1, w2, b2, w3, b3, mode="bf16t")
+        b, _ = dcf.ops.fusion_fwd(bev, Th.float(), knn, sc["geom"], w1, w2, b2, w3, b3, mode="bf16")
+        assert torch.equal(a, b), f"C={sc['C']}"
+        io = bev.clone()
+        dcf.ops.fusion_fwd(io, Th, knn, sc["geom"], w1, w2, b2, w3, b3, mode="bf16t", out=io)
+        assert torch.equal(io, a), f"C={sc['C']} in place"
+        with pytest.raises(TypeError, match="bfloat16"):
+            dcf.ops.fusion_fwd(bev, Th.float(), knn, sc["geom"], w1, w2, b2, w3, b3, mode="bf16t")
+
+
+def test_bf16_tables_mode_is_inference_only(dcf):
+    wl = dcf.synthetic.make_workload("tiny", seed=33, c_img=32, img_hw=(24, 32))
+    sc = wl["scales"][0]
+    layer = dcf.ContinuousFusion(32, sc["C"], k=wl["k"], radius=wl["radius"], geom=sc["geom"], mode="bf16t").cuda()
+    frames = dcf.prepare_frames(dev(wl["points"]), dev(wl["num_points"]), dev(wl["img_feat"]), config=wl["config"], calib=wl["calib"])
+    with torch.no_grad():
+        out = layer(dev(sc["bev"]), frames=frames)
+    assert out.shape == sc["bev"].shape and bool(torch.isfinite(out).all())
+    with pytest.raises(RuntimeError, match="inference only"):
+        layer(dev(sc["bev"]), frames=frames)
+
+
 def test_fusion_channels_last_map_equals_nchw(dcf):
     wl = dcf.synthetic.make_workload("tiny", seed=14, c_img=64, img_hw=(30, 40))
     a, _ = cuda_fusion(dcf, wl, "simt", channels_last=False)

@@ -42,13 +42,15 @@ def test_knn_every_k(dcf, oracle, K):
     assert np.array_equal(got, oracle_knn(oracle, wl, sc, k=K))
 
 
+@pytest.mark.parametrize("K", [None, 9])   # the workload's K (row-major gather) and K >= 8 (centre-out gather of the patch kernel)
 @pytest.mark.parametrize("radius,cell", [(0.3, 0.5), (2.0, 0.25), (2.0, 1.7), (5.0, 0.5), (40.0, 2.0)])
-def test_knn_radius_and_bucket_pitch(dcf, oracle, radius, cell):
+def test_knn_radius_and_bucket_pitch(dcf, oracle, radius, cell, K):
     """Result must not depend on the bucket pitch; radius from 'mostly empty' to 'everything is a candidate'."""
     wl = dcf.synthetic.make_workload("tiny", seed=4)
-    sc = wl["scales"][1]
-    got, _ = cuda_knn(dcf, wl, sc, cell=cell, radius=radius)
-    assert np.array_equal(got, oracle_knn(oracle, wl, sc, radius=radius))
+    kw = {} if K is None else {"k": K}
+    for sc in wl["scales"][:2]:   # scale 0: patch kernel, scale 1 onwards: whichever the patch-size rule picks
+        got, _ = cuda_knn(dcf, wl, sc, cell=cell, radius=radius, **kw)
+        assert np.array_equal(got, oracle_knn(oracle, wl, sc, radius=radius, **kw))
 
 
 def test_knn_ties_duplicates_and_lattice(dcf, oracle):
@@ -89,11 +91,12 @@ def test_knn_empty_and_ragged_frames(dcf, oracle):
     wl["points"][3] = np.tile(full[:n_full], (reps, 1))[:N] + np.float32(0.001) * np.arange(N, dtype=np.float32)[:, None]
     wl["num_points"][:] = [0, 1, 2, N]
     sc = wl["scales"][0]
-    got, (start, _) = cuda_knn(dcf, wl, sc, k=3)
-    ref = oracle_knn(oracle, wl, sc, k=3)
-    assert np.array_equal(got, ref)
-    assert (got[0] == -1).all() and start[0].max() == 0
-    assert (got[1] <= 0).all() and (got[2] <= 1).all()
+    for K in (3, 12):
+        got, (start, _) = cuda_knn(dcf, wl, sc, k=K)
+        ref = oracle_knn(oracle, wl, sc, k=K)
+        assert np.array_equal(got, ref)
+        assert (got[0] == -1).all() and start[0].max() == 0
+        assert (got[1] <= 0).all() and (got[2] <= 1).all()
 
 
 def test_knn_rejects_bad_arguments(dcf):

@@ -1380,6 +1380,9 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
 // into one of two buffers, one thread issues the K = Ci MMAs into one of two TMEM accumulators, and the epilogue of the
 // previous chunk (rank-3 offset + bias, write T) runs under them.
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef CF_L1_PREFETCH
+#define CF_L1_PREFETCH 1
+#endif
 constexpr int kMaxScales = 8, kMaxChunks = 24;
 constexpr int kMultiThreads = 544;   // 16 worker warps + the MMA issuer warp
 constexpr int kStageGroup = kTile * 128;              // one staged block: 128 rows of 128 bytes (32 fp32 / 64 bf16 columns), SWIZZLE_128B
@@ -1518,6 +1521,18 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
         const int32_t n_pts = valid_points(p.num_points, b, p.N);
         if (m0 >= n_pts) continue;  // uniform across the CTA
         const bool full = MS::kStaged && p.tma_out && m0 + kTile <= n_pts;
+#if CF_L1_PREFETCH
+        // the feature rows of this CTA's next tile start their way from DRAM into L2 now, one tile ahead of their A-operand build
+        if (tid == kIssuer) {
+            const int64_t nt = tile + gridDim.x;
+            if (nt < tiles_total) {
+                const int nb = (int)(nt / p.tiles_per_frame);
+                const int32_t nm0 = (int32_t)(nt - (int64_t)nb * p.tiles_per_frame) * kTile;
+                const int32_t rows = min(kTile, valid_points(p.num_points, nb, p.N) - nm0);
+                if (rows > 0) tc::bulk_prefetch_l2(p.feat + ((size_t)nb * p.N + nm0) * Ci, (uint32_t)(rows * Ci * 4));
+            }
+        }
+#endif
         // ---- A tile, once for all scales (same lane mapping as k_point_mlp1_tc).  The feature rows stream from DRAM:
         // the loads of a batch of items are all issued before the first one is split and stored ------------------------
         const float *fb = p.feat + ((size_t)b * p.N + m0) * Ci;

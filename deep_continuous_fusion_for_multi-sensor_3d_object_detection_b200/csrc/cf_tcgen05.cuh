@@ -181,6 +181,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint
                  "r"(bar_addr)
                  : "memory");
 }
+// L2 prefetch of a contiguous global range by the TMA engine (no destination in the SM): `bytes` a multiple of 16, 16-byte aligned
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 template <int N>

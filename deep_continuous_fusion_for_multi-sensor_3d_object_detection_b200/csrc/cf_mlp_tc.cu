@@ -1384,7 +1384,14 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
 #define CF_L1_PREFETCH 1
 #endif
 constexpr int kMaxScales = 8, kMaxChunks = 24;
-constexpr int kMultiThreads = 544;   // 16 worker warps + the MMA issuer warp
+// 8 worker warps + the MMA issuer warp.  With 16 worker warps the kernel alone is a little faster, but its CTA then holds 52 k of
+// the SM's 64 k registers and the KNN search, which runs beside it on another stream, gets one block per SM; with 8 it gets
+// three (measured: configs[2] step 3.99 -> 3.93 ms, configs[1] 0.903 -> 0.895 ms; a high-priority stream for this kernel
+// instead made both slower).
+#ifndef CF_MULTI_THREADS
+#define CF_MULTI_THREADS 288
+#endif
+constexpr int kMultiThreads = CF_MULTI_THREADS;
 constexpr int kStageGroup = kTile * 128;              // one staged block: 128 rows of 128 bytes (32 fp32 / 64 bf16 columns), SWIZZLE_128B
 // Per split count: output columns per chunk (UMMA N) and whether full tiles are staged for TMA stores.  The staged path pays
 // when the tables leave for DRAM (bf16 mode at configs[2]: 2.5 GB per step); with two splits the operands leave no room
@@ -1433,8 +1440,8 @@ template <int NS, bool TH = false>
 __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp1MultiParams p, const __grid_constant__ Mlp1Maps maps)
 {
     using MS = MultiShape<NS, TH>;
-    // warps 0-15: workers (operand build, epilogues; 4 threads per row split the columns of a chunk);
-    // warp 16: one elected lane streams the weight chunks (two cp.async.bulk per chunk: TMA engine, mbarrier complete_tx) and
+    // warps 0 .. NW-1: workers (operand build, epilogues; NT / 128 threads per row split the columns of a chunk);
+    // warp NW: one elected lane streams the weight chunks (two cp.async.bulk per chunk: TMA engine, mbarrier complete_tx) and
     // issues the MMAs (descriptors in uniform registers), so the tcgen05.mma of a chunk never sit in front of an epilogue
     constexpr int NT = kMultiThreads - 32, NW = NT / 32, kIssuer = NT, kColGroups = NT / kTile;
     constexpr int kChunkW = MS::kChunkW, kStageSet = MS::kStageSet, kStageBytes = MS::kStageBytes, kGroupCols = MS::kGroupCols;

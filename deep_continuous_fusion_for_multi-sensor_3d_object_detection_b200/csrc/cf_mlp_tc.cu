@@ -46,6 +46,7 @@ struct Tuning {
     bool debug_launch = false;    // CF_DEBUG_LAUNCH: print the launch shape
     bool no_skew = false;         // CF_NO_SKEW: never use the double-buffered kernel
     bool seg = false;             // CF_SEG: route the fine scales through the segment-tile kernel (cf_fusion_seg.cu)
+    bool no_tma_store = false;    // CF_NO_TMA_STORE: the layer-1 kernel stores every tile directly (the path taken without tensor maps)
     long long compact_min_tiles = -1;   // CF_COMPACT_MIN_TILES
 };
 static const Tuning &tuning()
@@ -56,6 +57,7 @@ static const Tuning &tuning()
         v.debug_launch = getenv("CF_DEBUG_LAUNCH") != nullptr;
         v.no_skew = getenv("CF_NO_SKEW") != nullptr;
         v.seg = getenv("CF_SEG") != nullptr;
+        v.no_tma_store = getenv("CF_NO_TMA_STORE") != nullptr;
         if (const char *e = getenv("CF_COMPACT_MIN_TILES")) v.compact_min_tiles = atoll(e);
         return v;
     }();
@@ -2046,10 +2048,12 @@ int point_mlp1_multi_tc(const float *d_feat, const float *d_points, const int64_
     if (smem > 225 * 1024) return CF_ERR_UNSUPPORTED;
     Mlp1Maps maps;
     memset(&maps, 0, sizeof(maps));
-    p.tma_out = stage_bytes > 0;
+    p.tma_out = stage_bytes > 0 && !tuning().no_tma_store;
     for (int s = 0; s < n_scales; ++s)
         if (((uintptr_t)h_T[s] & 15u) != 0) p.tma_out = 0;
-    for (int s = 0; s < n_scales && p.tma_out; ++s) CF_TRY(make_table_map(&maps.m[s], h_T[s], h_C[s], N, B, th));
+    for (int s = 0; s < n_scales && p.tma_out; ++s)
+        if (make_table_map(&maps.m[s], h_T[s], h_C[s], N, B, th) != CF_OK) p.tma_out = 0;   // no tensor maps (old driver): direct stores
+    if (tuning().debug_launch) fprintf(stderr, "k_point_mlp1_multi<%d,%d>: %d chunks, staged TMA stores %d\n", NS, (int)th, chunks, p.tma_out);
     auto kern = NS == 2 ? k_point_mlp1_multi<2> : th ? k_point_mlp1_multi<1, true> : k_point_mlp1_multi<1>;
     CF_TRY(cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "k_point_mlp1_multi smem attribute"));

@@ -121,6 +121,45 @@ def test_bf16_tables_layer1_is_the_rounded_fp32_table(dcf):
         dcf.ops.point_mlp1_multi(feat, pts, cnt, W1s, b1s, pkt, mode="bf16t", outs=[torch.zeros(B, N, c, device="cuda") for c in Cs])
 
 
+def test_layer1_direct_store_path_equals_tma_store_path():
+    """CF_NO_TMA_STORE=1 (read once per process, hence the child process) makes the layer-1 kernel store every tile directly,
+    the path it takes when the driver has no tensor maps: same bits as the staged TMA stores, in "bf16" and "bf16t"."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import dcf_b200 as dcf
+torch.manual_seed(41)
+B, N, Ci = 2, 700, 128
+feat = torch.randn(B, N, Ci, device="cuda"); pts = torch.randn(B, N, 3, device="cuda") * 20
+cnt = torch.tensor([700, 389], dtype=torch.int64, device="cuda")
+Cs = [32, 64, 128, 192, 256]
+W1s = [torch.randn(c, Ci + 3, device="cuda") * 0.1 for c in Cs]; b1s = [torch.randn(c, device="cuda") for c in Cs]
+for mode in ("bf16", "bf16t"):
+    pk = [dcf.ops.PackedWeights().w1(w, mode) for w in W1s]
+    outs = dcf.ops.point_mlp1_multi(feat, pts, cnt, W1s, b1s, pk, mode=mode,
+                                    outs=[torch.zeros(B, N, c, device="cuda", dtype=dcf.ops.table_dtype(mode)) for c in Cs])
+    torch.cuda.synchronize()
+    torch.save([o.cpu() for o in outs], sys.argv[1] + mode + ".pt")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        logs = {}
+        for tag, env in (("tma_", {}), ("direct_", {"CF_NO_TMA_STORE": "1"})):
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag)], capture_output=True, text=True, timeout=300,
+                               env=dict(os.environ, CF_DEBUG_LAUNCH="1", **env))
+            assert r.returncode == 0, r.stderr[-2000:]
+            logs[tag] = r.stderr
+        assert "staged TMA stores 1" in logs["tma_"] and "staged TMA stores 0" in logs["direct_"] and "staged TMA stores 1" not in logs["direct_"]
+        for mode in ("bf16", "bf16t"):
+            a = torch.load(os.path.join(d, "tma_" + mode + ".pt"))
+            b = torch.load(os.path.join(d, "direct_" + mode + ".pt"))
+            for x, y in zip(a, b):
+                assert torch.equal(x, y) and float(x[1, 389:].abs().max()) == 0.0 and float(x[0].abs().max()) > 0
+
+
 @pytest.mark.parametrize("name,seed", [("tiny", 31), ("yaml", 32)])
 def test_bf16_tables_fused_layer_equals_bf16_mode_on_the_rounded_table(dcf, name, seed):
     """The fused kernels of "bf16t" differ from "bf16" only in how a table row is loaded: fed the same (bf16-representable)

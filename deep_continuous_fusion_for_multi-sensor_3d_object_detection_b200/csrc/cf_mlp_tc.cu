@@ -1359,9 +1359,14 @@ __global__ void __launch_bounds__(kTile * Mlp1Shape<C>::G) k_point_mlp1_tc(const
                 for (int q4 = 0; q4 < 8; ++q4) {
                     float o[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int c = cc * 32 + q4 * 4 + i;
-                        o[i] = z[q4 * 4 + i] + (swx[c] * px + swy[c] * py + swz[c] * pz) + sb1[c];
+                    for (int i = 0; i < 2; ++i) {   // the same packed sequence as k_point_mlp1_multi (bit-identical tables)
+                        const int c = cc * 32 + q4 * 4 + 2 * i;
+                        float2 t = tc::fmul2(make_float2(swx[c], swx[c + 1]), make_float2(px, px));
+                        t = tc::ffma2(make_float2(swy[c], swy[c + 1]), make_float2(py, py), t);
+                        t = tc::ffma2(make_float2(swz[c], swz[c + 1]), make_float2(pz, pz), t);
+                        t = tc::fadd2(tc::fadd2(make_float2(z[q4 * 4 + 2 * i], z[q4 * 4 + 2 * i + 1]), t), make_float2(sb1[c], sb1[c + 1]));
+                        o[2 * i] = t.x;
+                        o[2 * i + 1] = t.y;
                     }
                     dst[q4] = make_float4(o[0], o[1], o[2], o[3]);
                 }
@@ -1471,10 +1476,11 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 2 * kChunkW);
     for (int s = 0; s < p.n_scales; ++s) {
         const int C = p.C[s];
-        float4 *f = reinterpret_cast<float4 *>(sF + p.foff[s]);   // per output channel: (b1, wx, wy, wz)
+        float *f = sF + p.foff[s];   // per PAIR of output channels (c, c + 1): b1 b1 | wx wx | wy wy | wz wz (packed fp32 math)
         for (int c = tid; c < C; c += NT + 32) {
             const float *w = p.W1[s] + (size_t)c * (Ci + 3) + Ci;
-            f[c] = make_float4(__ldg(p.b1[s] + c), __ldg(w), __ldg(w + 1), __ldg(w + 2));
+            float *fp = f + (c >> 1) * 8 + (c & 1);
+            fp[0] = __ldg(p.b1[s] + c); fp[2] = __ldg(w); fp[4] = __ldg(w + 1); fp[6] = __ldg(w + 2);
         }
     }
     tc::fence_before_sync();
@@ -1597,9 +1603,14 @@ __global__ void __launch_bounds__(kMultiThreads, 1) k_point_mlp1_multi(const Mlp
                     for (int q8 = 0; q8 < 2; ++q8) {
                         float o[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 w = f[n0 + c + q8 * 8 + i];
-                            o[i] = z[q8 * 8 + i] + (w.y * px + w.z * py + w.w * pz) + w.x;
+                        for (int i = 0; i < 4; ++i) {   // two columns per FMUL2 / FFMA2 / FADD2: z + ((wx px + wy py) + wz pz) + b1
+                            const float4 fa = f[(n0 + c + q8 * 8) + 2 * i], fb = f[(n0 + c + q8 * 8) + 2 * i + 1];
+                            float2 t = tc::fmul2(make_float2(fa.z, fa.w), make_float2(px, px));
+                            t = tc::ffma2(make_float2(fb.x, fb.y), make_float2(py, py), t);
+                            t = tc::ffma2(make_float2(fb.z, fb.w), make_float2(pz, pz), t);
+                            t = tc::fadd2(tc::fadd2(make_float2(z[q8 * 8 + 2 * i], z[q8 * 8 + 2 * i + 1]), t), make_float2(fa.x, fa.y));
+                            o[2 * i] = t.x;
+                            o[2 * i + 1] = t.y;
                         }
                         if (TH) {   // 8 columns -> one 16-byte chunk of bf16 (round to nearest even)
                             const uint4 h = make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]),
